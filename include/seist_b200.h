@@ -1,0 +1,181 @@
+/*
+ * seist_b200 — C-ABI of the B200-native SeisT forward/backward hot path.
+ *
+ * The reference (senli1073/SeisT) is pure Python/PyTorch and has no FFI of its own; the interfaces
+ * these entry points replace are the torch.nn leaf modules its model calls
+ * (/root/reference/models/seist.py) — cited per op kind below — plus models/loss.py:32-56 (BCELoss),
+ * torch.nn.HuberLoss (models/loss.py:3) and the Adam step of training/train.py:304-308,109-111.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE pointer
+ * into memory owned by the caller (torch-allocated); all tensors are contiguous fp32 (N, C, L)
+ * ("NCL", sample axis contiguous) unless stated; every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*), never allocates, never synchronises and is CUDA-graph
+ * capturable.  Return value: 0 ok, <0 argument error, >0 cudaError_t.
+ *
+ * The network is executed as a *plan*: an array of SeistOp descriptors built once by the host
+ * (seist_b200/plan.py) and run by seist_plan_run().  A descriptor names its operands as *views*:
+ * a (channel-slice of a) materialised pre-BatchNorm tensor plus the BatchNorm / activation that
+ * the consumer applies on load.  BatchNorm statistics are accumulated by the producer's epilogue
+ * into the BN table, so a training-mode BN never costs its own pass over memory.
+ */
+#ifndef SEIST_B200_H_
+#define SEIST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEIST_ABI_VERSION 3
+#define SEIST_MAX_IN 3
+
+/* ---- BatchNorm table entry (nn.BatchNorm1d, models/seist.py:641) ---------------- */
+typedef struct SeistBN {
+  const float* gamma;    /* [C] weight */
+  const float* beta;     /* [C] bias */
+  float* running_mean;   /* [C] */
+  float* running_var;    /* [C] */
+  double* stat;          /* [2C] sum(x), sum(x^2) of the BN input over (N, L)  (all ranks)       */
+  double* gstat;         /* [2C] sum(du), sum(du * khat) of the gradient w.r.t. the BN output     */
+  float* dgamma;         /* [C] */
+  float* dbeta;          /* [C] */
+  double count;          /* elements per channel behind `stat` (global batch * L)                 */
+  int32_t C;
+  int32_t chain;         /* index of a second BN applied directly on top (attention.norm after
+                            aggr.norm, models/seist.py:95,374) or -1                              */
+  int32_t use_batch;     /* 1 train (batch statistics), 0 eval (running statistics)               */
+  int32_t is_chained;    /* 1: this entry is the *second* BN of a chain (statistics derived)      */
+  float eps;
+  float momentum;
+  float grad_scale;      /* multiplies dgamma/dbeta (1/world_size under data parallelism)         */
+  int32_t pad_;
+} SeistBN;
+
+/* ---- operand view ---------------------------------------------------------------------------- */
+typedef struct SeistView {
+  float* x;        /* base of the (N, Ct, L) tensor                                               */
+  float* g;        /* gradient buffer, same geometry: w.r.t. BN(x) if bn>=0 else w.r.t. x; or NULL */
+  int32_t Ct;      /* channels of the underlying buffer                                           */
+  int32_t c0;      /* first channel of the slice                                                  */
+  int32_t C;       /* channels in the slice (0 = view absent)                                     */
+  int32_t L;       /* samples                                                                     */
+  int32_t bn;      /* BN table index applied on load, -1 none                                     */
+  int32_t bn_c0;   /* channel offset of the slice inside that BN                                  */
+  int32_t act;     /* 0 none, 1 exact-erf GELU (models/seist.py:640)                              */
+  int32_t accum;   /* backward: 0 overwrite g, 1 add into g                                       */
+} SeistView;
+
+enum SeistOpKind {
+  /* generalised 1-D convolution: out = alpha(n)*[drop(conv(f(in)) + bias) + res_a] + res_b.
+     Covers nn.Conv1d k=1 (models/seist.py:86,107,111,130,142,182,225,287,351-364,429,451),
+     depthwise (:134-141), grouped (:215-222) and dense head convs (:536,546) with _auto_pad_1d
+     (:12-48); the input may be avg+max pooled (:80-81,93) or linearly up-sampled (:566);
+     channel concat (:192,315,500) is a multi-view input or a channel-sliced output;
+     Dropout/DropPath (:114,228,239,360-366,446,470,484) are the drop()/alpha() factors. */
+  SEIST_OP_CONV_FWD = 1,
+  SEIST_OP_CONV_BWD_DATA = 2,   /* gradient to the input views                                    */
+  SEIST_OP_CONV_BWD_W = 3,      /* dW, dbias                                                      */
+  SEIST_OP_RES_BWD = 4,         /* gradient to res_a / res_b                                      */
+  /* AttentionBlock core softmax((q/sqrt(E))^T k) v^T, models/seist.py:381-388 */
+  SEIST_OP_ATT_FWD = 5,
+  SEIST_OP_ATT_BWD_Q = 6,
+  SEIST_OP_ATT_BWD_KV = 7,
+  /* HeadRegression / HeadClassification: mean over L -> Linear -> act, models/seist.py:575-610 */
+  SEIST_OP_HEADVEC_FWD = 8,
+  SEIST_OP_HEADVEC_BWD = 9,
+  /* running-stat update / dgamma,dbeta for every BN of the table in one launch */
+  SEIST_OP_BN_FINALIZE_FWD = 10,
+  SEIST_OP_BN_FINALIZE_BWD = 11,
+  SEIST_OP_ZERO = 12            /* memset out.x[0 .. zero_bytes)                                   */
+};
+
+typedef struct SeistOp {
+  int32_t kind;
+  int32_t N;                    /* local batch */
+  const SeistBN* bn_table;      /* device copy of the BN table */
+  const uint64_t* step_seed;    /* device scalar mixed into every dropout stream (may be NULL)     */
+
+  SeistView in[SEIST_MAX_IN];   /* channel-concatenated inputs (ATT: q, k, v)                      */
+  SeistView res_a;
+  SeistView res_b;
+  SeistView out;                /* out.bn/bn_c0: BN whose statistics the epilogue accumulates;
+                                   out.g: gradient w.r.t. BN(out) (backward)                       */
+  float* out_dxd;               /* gradient w.r.t. out directly (backward), or NULL                */
+
+  const float* W;               /* [Cout, Cin/groups, k]                                           */
+  const float* bias;            /* [Cout] or NULL                                                  */
+  float* dW;
+  float* dbias;
+
+  int32_t n_in;
+  int32_t Cin;                  /* sum of in[].C                                                   */
+  int32_t Cout;
+  int32_t k;
+  int32_t stride;
+  int32_t pad_left;
+  int32_t groups;
+  int32_t pool;                 /* >1: input is AvgPool1d(pool,ceil)+MaxPool1d(pool,ceil) of the view */
+  int32_t up_src_L;             /* >0: input is F.interpolate(linear) of a view of this length      */
+  int32_t L_in;                 /* conv-input length (after pool / upsample, before padding)        */
+  int32_t L_out;
+  int32_t out_act;              /* 0 none, 1 sigmoid, 2 softmax (HEADVEC only)                      */
+  float out_scale;              /* HEADVEC: ScaledActivation factor                                 */
+
+  float p_elem;                 /* nn.Dropout on conv(...)+bias                                     */
+  float p_path;                 /* DropPath on the same quantity (per sample)                       */
+  float p_alpha;                /* outer DropPath alpha(n) (MPTL gconv_droppath)                    */
+  uint32_t seed_elem;
+  uint32_t seed_path;
+  uint32_t seed_alpha;
+
+  /* attention */
+  float* lse;                   /* [N, heads, Lq] log-sum-exp saved by the forward                  */
+  float* delta;                 /* [N, heads, Lq] scratch for the backward                          */
+  int32_t heads;
+  float p_attn;
+  uint32_t seed_attn;
+  int32_t pad0_;
+
+  uint64_t zero_bytes;          /* SEIST_OP_ZERO */
+  int32_t n_bn;                 /* BN_FINALIZE: entries in bn_table                                 */
+  int32_t pad1_;
+} SeistOp;
+
+/* ---- entry points ---------------------------------------------------------------------------- */
+int seist_abi_version(void);
+uint64_t seist_sizeof_op(void);
+uint64_t seist_sizeof_bn(void);
+const char* seist_last_error(void);
+/* number of kernel launches issued by this library since load (bench `gpu_launches`) */
+uint64_t seist_launch_count(void);
+
+/* run ops[0..n) in order on `stream` */
+int seist_plan_run(const SeistOp* ops, int32_t n, void* stream);
+
+/* BCELoss(weight) with eps inside the logs — models/loss.py:48-56.  preds/targets (N,C,L);
+   weight [C]; loss_sum: device double accumulator (zeroed by the call); *loss_out = sum / numel. */
+int seist_bce_fwd(const float* preds, const float* targets, const float* weight, int64_t N, int32_t C,
+                  int64_t L, float eps, double* loss_sum, float* loss_out, void* stream);
+/* dpreds = gout * dloss/dpreds  (gout: device scalar, upstream gradient of the mean loss) */
+int seist_bce_bwd(const float* preds, const float* targets, const float* weight, const float* gout,
+                  int64_t N, int32_t C, int64_t L, float eps, float* dpreds, void* stream);
+/* torch.nn.HuberLoss(delta) mean — models/loss.py:3, config.py:158 */
+int seist_huber_fwd(const float* preds, const float* targets, int64_t numel, float delta,
+                    double* loss_sum, float* loss_out, void* stream);
+int seist_huber_bwd(const float* preds, const float* targets, const float* gout, int64_t numel,
+                    float delta, float* dpreds, void* stream);
+
+/* torch.optim.Adam / AdamW (decoupled=1) single fused update over one flat buffer —
+   training/train.py:304-316.  lr and step are device scalars so the call is graph-replayable. */
+int seist_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                    const float* lr, const float* step, float beta1, float beta2, float eps,
+                    float weight_decay, int32_t decoupled, float grad_scale, void* stream);
+
+/* *seed += 1 (device scalar), keeps dropout streams distinct across graph replays */
+int seist_advance_seed(uint64_t* seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEIST_B200_H_ */
