@@ -1,0 +1,106 @@
+// C-ABI entry points and the plan executor (include/seist_b200.h).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+namespace seist {
+
+static char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+static int g_sm_count = 0;
+
+void set_error(const char* msg) {
+  std::strncpy(g_err, msg, sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+}
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    std::snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+int launch_conv_fwd(const SeistOp& op, cudaStream_t s);
+int launch_conv_bwd_data(const SeistOp& op, cudaStream_t s);
+int launch_conv_bwd_w(const SeistOp& op, cudaStream_t s, int sm_count);
+int launch_res_bwd(const SeistOp& op, cudaStream_t s);
+int launch_att_fwd(const SeistOp& op, cudaStream_t s);
+int launch_att_bwd_q(const SeistOp& op, cudaStream_t s);
+int launch_att_bwd_kv(const SeistOp& op, cudaStream_t s);
+int launch_headvec_fwd(const SeistOp& op, cudaStream_t s);
+int launch_headvec_bwd(const SeistOp& op, cudaStream_t s);
+int launch_bn_finalize(const SeistOp& op, bool fwd, cudaStream_t s);
+
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
+      g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+static int validate_conv(const SeistOp& op) {
+  if (op.groups <= 0 || op.Cin % op.groups || op.Cout % op.groups) { set_error("conv: channels not divisible by groups"); return -2; }
+  if (op.k < 1 || op.stride < 1 || op.N < 1 || op.L_out < 1) { set_error("conv: bad geometry"); return -2; }
+  if (op.n_in < 1 || op.n_in > SEIST_MAX_IN) { set_error("conv: bad n_in"); return -2; }
+  if ((op.pool > 1 || op.up_src_L > 0) && op.n_in != 1) { set_error("conv: pool/upsample need a single input view"); return -2; }
+  if (op.pool > 1 && (op.k != 1 || op.up_src_L > 0)) { set_error("conv: pool only with k=1"); return -2; }
+  if (op.N > 65535) { set_error("conv: batch > 65535 per launch"); return -2; }
+  return 0;
+}
+
+static int run_one(const SeistOp& op, cudaStream_t s) {
+  switch (op.kind) {
+    case SEIST_OP_CONV_FWD: { int v = validate_conv(op); return v ? v : launch_conv_fwd(op, s); }
+    case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); return v ? v : launch_conv_bwd_data(op, s); }
+    case SEIST_OP_CONV_BWD_W: { int v = validate_conv(op); return v ? v : launch_conv_bwd_w(op, s, sm_count()); }
+    case SEIST_OP_RES_BWD: return launch_res_bwd(op, s);
+    case SEIST_OP_ATT_FWD: return launch_att_fwd(op, s);
+    case SEIST_OP_ATT_BWD_Q: return launch_att_bwd_q(op, s);
+    case SEIST_OP_ATT_BWD_KV: return launch_att_bwd_kv(op, s);
+    case SEIST_OP_HEADVEC_FWD: return launch_headvec_fwd(op, s);
+    case SEIST_OP_HEADVEC_BWD: return launch_headvec_bwd(op, s);
+    case SEIST_OP_BN_FINALIZE_FWD: return launch_bn_finalize(op, true, s);
+    case SEIST_OP_BN_FINALIZE_BWD: return launch_bn_finalize(op, false, s);
+    case SEIST_OP_ZERO: {
+      cudaError_t e = cudaMemsetAsync(op.out.x, 0, op.zero_bytes, s);
+      if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
+      return 0;
+    }
+    default: set_error("unknown op kind"); return -1;
+  }
+}
+
+}  // namespace seist
+
+extern "C" {
+
+int seist_abi_version(void) { return SEIST_ABI_VERSION; }
+uint64_t seist_sizeof_op(void) { return sizeof(SeistOp); }
+uint64_t seist_sizeof_bn(void) { return sizeof(SeistBN); }
+const char* seist_last_error(void) { return seist::g_err; }
+uint64_t seist_launch_count(void) { return seist::g_launches.load(); }
+
+int seist_plan_run(const SeistOp* ops, int32_t n, void* stream) {
+  if (ops == nullptr || n < 0) { seist::set_error("plan_run: bad arguments"); return -1; }
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = 0; i < n; ++i) {
+    int rc = seist::run_one(ops[i], s);
+    if (rc != 0) {
+      char buf[600];
+      std::snprintf(buf, sizeof(buf), "op %d (kind %d): %s", i, ops[i].kind, seist::g_err);
+      seist::set_error(buf);
+      return rc;
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+// Shared device helpers for the seist_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/seist_b200.h"
+
+#define SEIST_ACT_GELU 1
+#define SEIST_OUT_SIGMOID 1
+#define SEIST_OUT_SOFTMAX 2
+
+namespace seist {
+
+// ---- launch bookkeeping (api.cu) -------------------------------------------------------------
+void note_launch();
+int check_launch(const char* what);
+void set_error(const char* msg);
+
+// ---- math -------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- counter-based RNG (mirrored by oracle/plan_interp.py::rng_u32) ---------------------------
+__device__ __forceinline__ uint32_t rng_u32(uint64_t step_seed, uint32_t stream, uint64_t idx) {
+  uint64_t z = step_seed * 0xD1342543DE82EF95ull + (((uint64_t)stream << 32) | 0x9E3779B9ull);
+  z += idx * 0x9E3779B97F4A7C15ull;
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+__device__ __forceinline__ uint32_t drop_threshold(float p) {
+  return (uint32_t)fminf(p * 4294967296.0f, 4294967040.0f);
+}
+// 1/(1-p) if kept else 0
+__device__ __forceinline__ float keep_scale(float p, uint64_t seed, uint32_t stream, uint64_t idx) {
+  return rng_u32(seed, stream, idx) >= drop_threshold(p) ? 1.0f / (1.0f - p) : 0.0f;
+}
+__device__ __forceinline__ uint64_t load_seed(const uint64_t* p) { return p ? *p : 0ull; }
+
+// ---- BatchNorm coefficient algebra (mirrored by oracle/plan_interp.py) ------------------------
+__device__ __forceinline__ void bn_moments(const SeistBN& e, int c, double& mean, double& var) {
+  if (e.use_batch) {
+    mean = e.stat[c] / e.count;
+    var = e.stat[e.C + c] / e.count - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+  } else {
+    mean = (double)e.running_mean[c];
+    var = (double)e.running_var[c];
+  }
+}
+
+// BN(x) = scale * x + shift, a chained second BN folded in
+__device__ __forceinline__ void bn_fwd_coef(const SeistBN* tab, int bn, int c, float& scale, float& shift) {
+  const SeistBN& e = tab[bn];
+  double mean, var;
+  bn_moments(e, c, mean, var);
+  const double g1 = e.gamma[c], b1 = e.beta[c];
+  const double s1 = g1 * rsqrt(var + (double)e.eps);
+  const double t1 = b1 - mean * s1;
+  if (e.chain >= 0) {
+    const SeistBN& e2 = tab[e.chain];
+    double mean2, var2;
+    if (e.use_batch) {
+      mean2 = b1;
+      var2 = s1 * s1 * var;
+    } else {
+      mean2 = (double)e2.running_mean[c];
+      var2 = (double)e2.running_var[c];
+    }
+    const double s2 = (double)e2.gamma[c] * rsqrt(var2 + (double)e2.eps);
+    scale = (float)(s2 * s1);
+    shift = (float)(s2 * (t1 - mean2) + (double)e2.beta[c]);
+  } else {
+    scale = (float)s1;
+    shift = (float)t1;
+  }
+}
+
+// khat = (x - mu) * istd : normalised input of the (first) BN, basis of gstat's second sum
+__device__ __forceinline__ void bn_khat_coef(const SeistBN* tab, int bn, int c, float& mu, float& istd) {
+  const SeistBN& e = tab[bn];
+  double mean, var;
+  bn_moments(e, c, mean, var);
+  mu = (float)mean;
+  istd = (float)rsqrt(var + (double)e.eps);
+}
+
+// d/dx = A * du + Bx * x + Cc   (du: gradient w.r.t. the BN output)
+__device__ __forceinline__ void bn_bwd_coef(const SeistBN* tab, int bn, int c, float& A, float& Bx, float& Cc) {
+  const SeistBN& e = tab[bn];
+  double mean, var;
+  bn_moments(e, c, mean, var);
+  const double eps = e.eps, cnt = e.count;
+  const double istd = rsqrt(var + eps);
+  const double g1 = e.gamma[c];
+  const double S1 = e.gstat[c], S2 = e.gstat[e.C + c];
+  double a, kc, c0;
+  if (e.chain < 0) {
+    a = g1 * istd;
+    kc = -a * S2 / cnt;
+    c0 = -a * S1 / cnt;
+  } else {
+    const SeistBN& e2 = tab[e.chain];
+    const double g2 = e2.gamma[c];
+    const double vk = var * istd * istd;
+    const double istd2 = rsqrt(g1 * g1 * vk + (double)e2.eps);
+    const double dg1 = g2 * istd2 * S2 * (1.0 - g1 * g1 * istd2 * istd2 * vk);
+    a = g1 * istd * g2 * istd2;
+    kc = -g1 * istd * (g2 * istd2 * g1 * g1 * istd2 * istd2 * S2 / cnt + dg1 / cnt);
+    c0 = -a * S1 / cnt;
+  }
+  A = (float)a;
+  Bx = (float)(kc * istd);
+  Cc = (float)(c0 - kc * istd * mean);
+}
+
+// ---- views ------------------------------------------------------------------------------------
+// Resolve concatenated-input channel `ci` to (view index, channel inside the view).
+__device__ __forceinline__ int resolve_view(const SeistOp& op, int ci, int& cv) {
+  int v = 0;
+  cv = ci;
+#pragma unroll
+  for (int i = 0; i < SEIST_MAX_IN - 1; ++i) {
+    if (v == i && i + 1 < op.n_in && cv >= op.in[i].C) {
+      cv -= op.in[i].C;
+      v = i + 1;
+    }
+  }
+  return v;
+}
+
+__device__ __forceinline__ const float* view_row(const SeistView& v, int n, int c) {
+  return v.x + ((size_t)n * v.Ct + v.c0 + c) * (size_t)v.L;
+}
+__device__ __forceinline__ float* view_grad_row(const SeistView& v, int n, int c) {
+  return v.g + ((size_t)n * v.Ct + v.c0 + c) * (size_t)v.L;
+}
+__device__ __forceinline__ void view_coef(const SeistOp& op, const SeistView& v, int c, float& sc, float& sh) {
+  if (v.bn >= 0) {
+    bn_fwd_coef(op.bn_table, v.bn, v.bn_c0 + c, sc, sh);
+  } else {
+    sc = 1.0f;
+    sh = 0.0f;
+  }
+}
+
+// per-channel gradient prologue of the op's output: dOut = A*du + Bx*x + Cc + dxd (then sigmoid')
+struct OutGradCoef {
+  float A, Bx, Cc;
+};
+__device__ __forceinline__ OutGradCoef out_grad_coef(const SeistOp& op, int co) {
+  OutGradCoef k;
+  if (op.out.bn >= 0 && op.out.g != nullptr) {
+    bn_bwd_coef(op.bn_table, op.out.bn, op.out.bn_c0 + co, k.A, k.Bx, k.Cc);
+  } else {
+    k.A = 0.f;
+    k.Bx = 0.f;
+    k.Cc = 0.f;
+  }
+  return k;
+}
+__device__ __forceinline__ float out_grad_at(const SeistOp& op, const OutGradCoef& k, int n, int co, int l) {
+  const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)op.out.L + l;
+  float g = 0.f;
+  if (op.out_dxd != nullptr) g = op.out_dxd[off];
+  const bool has_bn = (op.out.bn >= 0 && op.out.g != nullptr);
+  if (has_bn || op.out_act == SEIST_OUT_SIGMOID) {
+    const float x = op.out.x[off];
+    if (has_bn) g += k.A * op.out.g[off] + k.Bx * x + k.Cc;
+    if (op.out_act == SEIST_OUT_SIGMOID) g *= x * (1.0f - x);
+  }
+  return g;
+}
+
+// deposit a per-channel pair of gstat partial sums (called by one lane per warp)
+__device__ __forceinline__ void gstat_add(const SeistOp& op, const SeistView& v, int c, float s1, float s2) {
+  const SeistBN& e = op.bn_table[v.bn];
+  atomicAdd(&e.gstat[v.bn_c0 + c], (double)s1);
+  atomicAdd(&e.gstat[e.C + v.bn_c0 + c], (double)s2);
+}
+
+}  // namespace seist

@@ -1,0 +1,150 @@
+"""Execution engine: owns the flat parameter state and the compiled plans of one model and runs
+them through the C-ABI (`seist_plan_run`) on the current CUDA stream.
+
+`Engine.forward` is what `SeismogramTransformer.forward` calls: it is autograd-compatible (the
+returned tensor carries a grad_fn whose backward runs the backward plan and deposits parameter
+gradients into views of one flat gradient buffer), works under `torch.no_grad()` / `.eval()`, and
+under data parallelism reduces SyncBatchNorm statistics across ranks between the producing and the
+consuming kernels (reference training/train.py:374 converts every BN to SyncBatchNorm).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib
+from . import plan as P
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _PlanFn(torch.autograd.Function):
+    """x -> y through the forward plan; backward runs the backward plan.  Parameter gradients are a
+    side effect (views of Engine.flat.G attached to `.grad`); `trigger` only keeps the node alive."""
+
+    @staticmethod
+    def forward(ctx, x, trigger, engine, plan):
+        ctx.engine, ctx.plan = engine, plan
+        y = engine.run_forward(plan, x)
+        return y.clone()
+
+    @staticmethod
+    def backward(ctx, dy):
+        ctx.engine.run_backward(ctx.plan, dy)
+        return None, None, None, None
+
+
+class Engine:
+    def __init__(self, model: nn.Module):
+        self.model = model
+        self.flat: Optional[P.FlatState] = None
+        self.plans: Dict[Tuple, P.Plan] = {}
+        self._trigger = None
+        self.last_plan: Optional[P.Plan] = None
+
+    # ---- lifecycle -------------------------------------------------------------------------------
+    def invalidate(self, release_flat: bool = False):
+        self.plans.clear()
+        self.last_plan = None
+        if release_flat:
+            self.flat = None
+
+    def _ensure_flat(self, device):
+        if self.flat is None or self.flat.device != device or not self.flat.valid():
+            self.plans.clear()
+            self.flat = P.FlatState(self.model, device)
+            self._trigger = torch.zeros(1, device=device, requires_grad=True)
+        return self.flat
+
+    def sync_world(self) -> int:
+        """World size over which BatchNorm statistics are shared (1 unless the BNs are SyncBatchNorm)."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        if any(isinstance(m, nn.SyncBatchNorm) for m in self.model.modules()):
+            return dist.get_world_size()
+        return 1
+
+    def get_plan(self, N: int, L: int, training: bool, need_backward: bool) -> P.Plan:
+        _lib.lib()   # fail loudly if the CUDA extension is missing
+        world = self.sync_world() if training else 1
+        key = (N, L, training, need_backward, world)
+        pl = self.plans.get(key)
+        if pl is None:
+            if len(self.plans) >= 4:      # plans own large arenas; keep the cache small
+                self.plans.pop(next(iter(self.plans)))
+            b = P.PlanBuilder(self.model, self.flat, N, L, training, world=world, need_backward=need_backward)
+            pl = P.finalize(b.build(), need_backward)
+            self.plans[key] = pl
+        return pl
+
+    # ---- execution -------------------------------------------------------------------------------
+    def _run_segments(self, plan: P.Plan, c_ops, segs, stat: torch.Tensor):
+        lib = _lib.lib()
+        base = ctypes.addressof(c_ops)
+        size = ctypes.sizeof(_lib.SeistOp)
+        for start, end, sync in segs:
+            for b in sync:
+                e = plan.bns[b]
+                dist.all_reduce(stat[e.st_off:e.st_off + 2 * e.C])
+            _lib.check(lib.seist_plan_run(base + start * size, end - start, _stream_ptr()), "seist_plan_run")
+
+    def run_forward(self, plan: P.Plan, x: torch.Tensor) -> torch.Tensor:
+        plan.x_in.x.copy_(x)
+        if plan.training:
+            plan.stat.zero_()
+        self._run_segments(plan, plan.c_fwd, plan.fwd_segments, plan.stat)
+        if plan.training:
+            self.flat.NBT[:len(plan.bns)] += 1
+        self.last_plan = plan
+        y = plan.y_out.x
+        return y if plan.y_out.L > 1 else y[:, :, 0]
+
+    def run_backward(self, plan: P.Plan, dy: torch.Tensor):
+        flat = self.flat
+        p0 = flat.params[0]
+        fresh = p0.grad is None or p0.grad.data_ptr() != flat.G.data_ptr() + 4 * flat.pref[self._name0].off
+        if fresh:
+            flat.G.zero_()
+        plan.gstat.zero_()
+        plan.y_out.dxd.copy_(dy.reshape(plan.y_out.dxd.shape))
+        self._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat)
+        for name, p in self._named:
+            if p.grad is None:
+                p.grad = flat.grad_view(name)
+            elif p.grad.data_ptr() != flat.G.data_ptr() + 4 * flat.pref[name].off:
+                p.grad = p.grad + flat.grad_view(name)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        model = self.model
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        if x.dim() != 3 or x.shape[1] != model.hp.in_channels:
+            raise ValueError(f"expected input of shape (N, {model.hp.in_channels}, L), got {tuple(x.shape)}")
+        self._ensure_flat(x.device)
+        if not hasattr(self, "_named") or self._named_flat is not self.flat:
+            self._named = list(model.named_parameters())
+            self._name0 = self._named[0][0]
+            self._named_flat = self.flat
+        N, _, L = x.shape
+        training = model.training
+        need_bwd = training and torch.is_grad_enabled()
+        plan = self.get_plan(N, L, training, need_bwd)
+        with torch.cuda.device(x.device):
+            if need_bwd:
+                return _PlanFn.apply(x, self._trigger, self, plan)
+            return self.run_forward(plan, x).clone()
+
+    # ---- data-parallel helpers -------------------------------------------------------------------
+    def allreduce_grads(self, average: bool = True):
+        """One collective over the flat gradient buffer (replaces DDP's bucketed reducer, C1)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat.G)
+            if average:
+                self.flat.G.div_(dist.get_world_size())

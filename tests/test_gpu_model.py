@@ -1,0 +1,124 @@
+"""-m gpu: the public API (create_model / forward / loss / backward) against the golden vectors the
+unmodified reference produced (tests/golden/make_golden.py) and against the oracle on fresh inputs.
+
+Tolerances (BASELINE.json north_star): outputs within 1e-3 relative (max-abs normalised) of the
+reference's CPU fp32 forward; P/S argmax indices bit-exact; gradients within 2e-3 of each tensor's
+max-abs with an absolute floor of 1e-5 x the largest gradient (several reference gradients are
+analytically zero — conv bias in front of BatchNorm, key bias under softmax — and hold only noise)."""
+import os
+
+import pytest
+import torch
+
+from oracle import seist_ref as R
+from seist_b200.models import BCELoss, HuberLoss, create_model
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ZERO = dict(path_drop_rate=0, attn_drop_rate=0, key_drop_rate=0, mlp_drop_rate=0, other_drop_rate=0)
+
+
+def _load(name):
+    g = torch.load(os.path.join(GOLD, f"{name}.pt"))
+    m = create_model(name, in_channels=3, in_samples=g["x"].shape[-1])
+    m.load_state_dict(g["state_dict"], strict=True)
+    return g, m.cuda()
+
+
+def _check_grads(model, ref_grads, rtol=2e-3, floor=1e-5):
+    gmax = max(v.abs().max().item() for v in ref_grads.values())
+    bad = []
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        ref = ref_grads[k]
+        err = (p.grad.cpu() - ref).abs().max().item()
+        if err > rtol * ref.abs().max().item() + floor * gmax:
+            bad.append((k, err, ref.abs().max().item()))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["seist_s_dpk", "seist_m_dpk", "seist_m_emg"])
+def test_eval_matches_reference_golden(name):
+    g, m = _load(name)
+    m.eval()
+    with torch.no_grad():
+        y = m(g["x"].cuda()).cpu()
+    ref = g["y_eval"]
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    if name.endswith("dpk"):
+        assert torch.equal(y[:, 1:].argmax(-1), ref[:, 1:].argmax(-1))   # P and S picks bit-exact
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["seist_s_dpk", "seist_m_dpk", "seist_m_emg"])
+def test_train_step_matches_reference_golden(name):
+    g, m = _load(name)
+    m.set_drop_rates(**ZERO)
+    m.train()
+    y = m(g["x"].cuda())
+    ref = g["y_train"]
+    assert (y.detach().cpu() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    if name.endswith("dpk"):
+        loss = BCELoss(weight=[[0.5], [1], [1]])(y, g["target"].cuda())
+    else:
+        loss = HuberLoss()(y, g["target"].cuda())
+    assert abs(loss.item() - g["loss"].item()) <= 1e-4 * abs(g["loss"].item())
+    loss.backward()
+    _check_grads(m, g["grads"])
+    sd = m.state_dict()
+    for k, b in g["buffers_after"].items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(b), k
+        else:
+            assert (sd[k].cpu() - b).abs().max().item() <= 1e-3 * (b.abs().max().item() + 1e-3), k
+
+
+@pytest.mark.gpu
+def test_l_model_and_batch_against_oracle():
+    """seist_l_dpk (no fixture): random non-degenerate parameters, train mode, oracle on the same inputs."""
+    from harness import randomize
+    torch.manual_seed(0)
+    m = randomize(create_model("seist_l_dpk", in_channels=3, in_samples=4096), seed=3)
+    m.set_drop_rates(**ZERO)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x, tgt = R.synth_waveforms(3, 4096, seed=11)
+    sd_g = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v)
+            for k, v in sd.items()}
+    y_ref, _ = R.forward(sd_g, x, R.spec_for("seist_l_dpk"), training=True)
+    loss_ref = R.bce_loss(y_ref, tgt)
+    loss_ref.backward()
+    m = m.cuda().train()
+    y = m(x.cuda())
+    assert (y.detach().cpu() - y_ref.detach()).abs().max().item() <= 1e-3 * y_ref.abs().max().item()
+    loss = BCELoss(weight=[[0.5], [1], [1]])(y, tgt.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
+    _check_grads(m, {k: sd_g[k].grad for k, _ in m.named_parameters()})
+
+
+@pytest.mark.gpu
+def test_dropout_statistics_and_determinism():
+    """Dropout/DropPath are not bit-matched to torch's Philox stream: check they are active,
+    reproducible for a fixed step seed and unbiased in the mean."""
+    g, m = _load("seist_s_dpk")
+    m.train()
+    x = g["x"].cuda()
+    eng = m.engine()
+    with torch.no_grad():
+        y0 = m(x)
+        seed = eng.last_plan.step_seed.clone()
+        y1 = m(x)
+        assert torch.equal(y0, y1)            # same step seed -> same masks
+        eng.last_plan.step_seed.add_(1)
+        y2 = m(x)
+        assert not torch.equal(y0, y2)
+        eng.last_plan.step_seed.copy_(seed)
+    assert torch.isfinite(y2).all()
+
+
+@pytest.mark.gpu
+def test_cpu_input_fails_loudly():
+    m = create_model("seist_s_dpk", in_channels=3, in_samples=1024)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 1024))
