@@ -1,0 +1,152 @@
+"""The training step of the reference (training/train.py:75-121) as one device-side program.
+
+Reference order: x.to(device) -> model(x) -> loss -> optimizer.zero_grad() -> loss.backward()
+-> optimizer.step() -> scheduler.step().  Here the whole step — dropout-seed advance, forward plan,
+fused loss forward+backward, backward plan, one flat gradient all-reduce, one fused Adam over the flat
+parameter buffer — is issued through the C-ABI on one stream and, on a single GPU, captured once into
+a CUDA graph and replayed (≈400 kernel launches per step would otherwise be CPU-launch bound).
+The per-step host syncs of the reference (`.item()`, barrier; train.py:124-135) are not on this path:
+`step()` returns the loss as a device scalar.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .models.loss import BCELoss, HuberLoss
+
+
+def cyclic_lr(it: int, base_lr=8e-5, max_lr=1e-3, up=2000, down=3000, gamma: Optional[float] = None) -> float:
+    """torch CyclicLR(mode='exp_range', cycle_momentum=False) as configured by training/train.py:343-354."""
+    total = up + down
+    ratio = up / total
+    cycle = math.floor(1 + it / total)
+    x = 1.0 + it / total - cycle
+    sf = x / ratio if x <= ratio else (x - 1) / (ratio - 1)
+    g = 1.0 if gamma is None else gamma ** it
+    return base_lr + (max_lr - base_lr) * sf * g
+
+
+class Trainer:
+    """Fused train step for a `SeismogramTransformer` (dpk -> BCELoss, reg -> HuberLoss)."""
+
+    def __init__(self, model, loss_fn=None, lr=8e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 decoupled_wd=False, lr_schedule=None, use_graph=True):
+        self.model = model
+        self.loss_fn = loss_fn
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.weight_decay, self.decoupled = weight_decay, decoupled_wd
+        self.lr_schedule = lr_schedule
+        self.use_graph = use_graph
+        self.it = 0
+        self.graph = None
+        self._shape = None
+        self.launches_per_step = 0
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    # ---- setup -----------------------------------------------------------------------------------
+    def _setup(self, x: torch.Tensor, target: torch.Tensor):
+        m = self.model
+        eng = m.engine()
+        dev = x.device
+        eng._ensure_flat(dev)
+        if not hasattr(eng, "_named") or eng._named_flat is not eng.flat:
+            eng._named = list(m.named_parameters())
+            eng._name0 = eng._named[0][0]
+            eng._named_flat = eng.flat
+        m.train()
+        N, _, L = x.shape
+        self.plan = eng.get_plan(N, L, True, True)
+        self.eng, self.flat = eng, eng.flat
+        n = self.flat.numel
+        if not hasattr(self, "exp_avg") or self.exp_avg.numel() != n:
+            self.exp_avg = torch.zeros(n, device=dev)
+            self.exp_avg_sq = torch.zeros(n, device=dev)
+            self.step_t = torch.zeros(1, device=dev)
+        self.lr_t = torch.full((1,), float(self.lr), device=dev)
+        self.x_static = self.plan.x_in.x
+        self.t_static = torch.empty_like(target, device=dev)
+        self.loss_acc = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.loss_out = torch.zeros((), device=dev)
+        self.gout = torch.ones(1, device=dev)
+        hp = m.hp
+        if self.loss_fn is None:
+            self.loss_fn = BCELoss(weight=[[0.5], [1], [1]]) if hp.head == "dpk" else HuberLoss()
+        if isinstance(self.loss_fn, BCELoss):
+            C = hp.head_out_channels
+            w = self.loss_fn.weight.to(dev, torch.float32)
+            self.wvec = (w.reshape(1).expand(C) if w.numel() == 1 else w.reshape(C)).contiguous()
+        elif not isinstance(self.loss_fn, HuberLoss):
+            raise NotImplementedError("Trainer fuses BCELoss (dpk) and HuberLoss (regression) only")
+        self._shape = (tuple(x.shape), tuple(target.shape))
+        self.graph = None
+        for _, p in eng._named:            # .grad are views of the flat gradient buffer
+            p.grad = None
+        for name, p in eng._named:
+            p.grad = self.flat.grad_view(name)
+
+    # ---- one step on the current stream ----------------------------------------------------------
+    def _issue(self):
+        lib = _lib.lib()
+        plan, eng, flat = self.plan, self.eng, self.flat
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.seist_advance_seed(plan.step_seed.data_ptr(), s))
+        plan.stat.zero_()
+        eng._run_segments(plan, plan.c_fwd, plan.fwd_segments, plan.stat)
+        flat.NBT[:len(plan.bns)] += 1
+        y, dy, t = plan.y_out.x, plan.y_out.dxd, self.t_static
+        if isinstance(self.loss_fn, BCELoss):
+            N, C, L = y.shape
+            _lib.check(lib.seist_bce_fwd(y.data_ptr(), t.data_ptr(), self.wvec.data_ptr(), N, C, L,
+                                         float(self.loss_fn._epsilon), self.loss_acc.data_ptr(),
+                                         self.loss_out.data_ptr(), s))
+            _lib.check(lib.seist_bce_bwd(y.data_ptr(), t.data_ptr(), self.wvec.data_ptr(), self.gout.data_ptr(),
+                                         N, C, L, float(self.loss_fn._epsilon), dy.data_ptr(), s))
+        else:
+            _lib.check(lib.seist_huber_fwd(y.data_ptr(), t.data_ptr(), y.numel(), self.loss_fn.delta,
+                                           self.loss_acc.data_ptr(), self.loss_out.data_ptr(), s))
+            _lib.check(lib.seist_huber_bwd(y.data_ptr(), t.data_ptr(), self.gout.data_ptr(), y.numel(),
+                                           self.loss_fn.delta, dy.data_ptr(), s))
+        flat.G.zero_()
+        plan.gstat.zero_()
+        eng._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat)
+        gscale = 1.0
+        if self.world > 1:
+            dist.all_reduce(flat.G)            # one collective for all 1.5 MB of gradients (C1)
+            gscale = 1.0 / self.world
+        self.step_t += 1
+        _lib.check(lib.seist_adam_step(flat.P.data_ptr(), flat.G.data_ptr(), self.exp_avg.data_ptr(),
+                                       self.exp_avg_sq.data_ptr(), flat.numel, self.lr_t.data_ptr(),
+                                       self.step_t.data_ptr(), self.betas[0], self.betas[1], self.eps,
+                                       self.weight_decay, 1 if self.decoupled else 0, gscale, s))
+
+    def step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """x (N,3,L), target on the device (or pinned host tensors: copied with non_blocking=True)."""
+        if self._shape != (tuple(x.shape), tuple(target.shape)) or not self.flat.valid():
+            self._setup(x if x.is_cuda else x.cuda(non_blocking=True), target)
+        self.x_static.copy_(x, non_blocking=True)
+        self.t_static.copy_(target.reshape(self.t_static.shape), non_blocking=True)
+        if self.lr_schedule is not None:
+            self.lr_t.fill_(float(self.lr_schedule(self.it)))
+        if self.use_graph and self.world == 1:
+            if self.graph is None:
+                before = _lib.lib().seist_launch_count()
+                self._issue()                    # warm-up (also sets kernel attributes)
+                torch.cuda.synchronize()
+                self.launches_per_step = int(_lib.lib().seist_launch_count() - before)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._issue()
+                self.graph = g
+            else:
+                self.graph.replay()
+        else:
+            before = _lib.lib().seist_launch_count()
+            self._issue()
+            self.launches_per_step = int(_lib.lib().seist_launch_count() - before)
+        self.it += 1
+        return self.loss_out

@@ -68,6 +68,8 @@ def test_ops_match_interpreter(name, N, L, training, drops):
     p_cpu.y_out.dxd.copy_(torch.randn(p_cpu.y_out.dxd.shape, generator=g) / p_cpu.y_out.dxd[0].numel() ** 0.5)
     for i, (bc, bg) in enumerate(zip(p_cpu.bwd_ops, p_gpu.bwd_ops)):
         push_state(p_cpu, p_gpu)
+        if bc.kind == _lib.ATT_BWD_KV:      # reads the `delta` scratch its sibling kernel produces
+            run_gpu_op(p_gpu, p_gpu.c_bwd, i - 1)
         it.run_bwd_op(bc)
         run_gpu_op(p_gpu, p_gpu.c_bwd, i)
         errs = []
