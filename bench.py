@@ -123,7 +123,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)      # host threads used by the CPU arm (torch intra-op pool)
     workload = f"{args.model} train step (fwd+BCE+bwd+Adam), batch {args.batch}/GPU x (3,{args.length}) fp32"
     config = {"workload": workload, "model": args.model, "per_gpu_batch": args.batch, "in_samples": args.length,
               "global_batch": args.batch * max(args.gpus, 1), "parallelism": f"dp{max(args.gpus, 1)}",
@@ -220,7 +220,7 @@ def main():
     # ---- dominant kernel roofline (rank 0) ---------------------------------------------------------
     roofline, step_roofline, cpu_baseline = None, None, None
     if rank == 0:
-        rows = time_ops(trainer.plan, reps=3)
+        rows = time_ops(trainer.plan, reps=2)
         tot = sum(r["ms"] for r in rows)
         rows.sort(key=lambda r: -r["ms"])
         top = rows[0]

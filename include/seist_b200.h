@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIST_ABI_VERSION 3
+#define SEIST_ABI_VERSION 4
 #define SEIST_MAX_IN 3
 
 /* ---- BatchNorm table entry (nn.BatchNorm1d, models/seist.py:641) ---------------- */
@@ -40,6 +40,9 @@ typedef struct SeistBN {
   double* gstat;         /* [2C] sum(du), sum(du * khat) of the gradient w.r.t. the BN output     */
   float* dgamma;         /* [C] */
   float* dbeta;          /* [C] */
+  float* coef;           /* [C][8] per-channel coefficients written by the BN_PREPARE ops:
+                            0 scale, 1 shift (BN(x) = scale*x + shift, chained BN folded in),
+                            2 mu, 3 istd (khat = (x-mu)*istd), 4 A, 5 Bx, 6 Cc (dx = A*du + Bx*x + Cc)  */
   double count;          /* elements per channel behind `stat` (global batch * L)                 */
   int32_t C;
   int32_t chain;         /* index of a second BN applied directly on top (attention.norm after
@@ -87,7 +90,11 @@ enum SeistOpKind {
   /* running-stat update / dgamma,dbeta for every BN of the table in one launch */
   SEIST_OP_BN_FINALIZE_FWD = 10,
   SEIST_OP_BN_FINALIZE_BWD = 11,
-  SEIST_OP_ZERO = 12            /* memset out.x[0 .. zero_bytes)                                   */
+  SEIST_OP_ZERO = 12,           /* memset out.x[0 .. zero_bytes)                                   */
+  /* per-channel coefficient tables of BN entries [bn_lo, bn_lo + n_bn): forward (scale, shift, mu,
+     istd) once the statistics are complete; backward (A, Bx, Cc) once gstat is complete */
+  SEIST_OP_BN_PREPARE_FWD = 13,
+  SEIST_OP_BN_PREPARE_BWD = 14
 };
 
 typedef struct SeistOp {
@@ -138,8 +145,8 @@ typedef struct SeistOp {
   int32_t pad0_;
 
   uint64_t zero_bytes;          /* SEIST_OP_ZERO */
-  int32_t n_bn;                 /* BN_FINALIZE: entries in bn_table                                 */
-  int32_t pad1_;
+  int32_t n_bn;                 /* BN_FINALIZE: entries in bn_table; BN_PREPARE: entries to prepare */
+  int32_t bn_lo;                /* BN_PREPARE: first entry                                          */
 } SeistOp;
 
 /* ---- entry points ---------------------------------------------------------------------------- */

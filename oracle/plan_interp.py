@@ -248,6 +248,8 @@ class Interp:
             f.out.buf.x[:, :, 0] = self._headvec_expr(f, self.value(f.ins[0])).float()
         elif f.kind == _lib.BN_FINALIZE_FWD:
             self.bn_finalize_fwd()
+        elif f.kind == _lib.BN_PREPARE_FWD:
+            pass        # coefficients are evaluated on the fly here (bn_fwd / bn_khat)
         else:
             raise ValueError(f.kind)
 
@@ -308,6 +310,8 @@ class Interp:
         p = self.p
         f = op.fwd
         G = p.flat.G
+        if op.kind == _lib.BN_PREPARE_BWD:
+            return      # coefficients are evaluated on the fly here (bn_bwd)
         if op.kind == _lib.ZERO:
             (op.out.buf.du if op.out.bn >= 0 else op.out.buf.dxd).zero_()
         elif op.kind == _lib.RES_BWD:

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libseist_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_IN = 3
 
 
@@ -17,7 +17,7 @@ class SeistBN(C.Structure):
         ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
         ("stat", C.c_void_p), ("gstat", C.c_void_p),
-        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("coef", C.c_void_p),
         ("count", C.c_double),
         ("C", C.c_int32), ("chain", C.c_int32), ("use_batch", C.c_int32), ("is_chained", C.c_int32),
         ("eps", C.c_float), ("momentum", C.c_float), ("grad_scale", C.c_float), ("pad_", C.c_int32),
@@ -48,7 +48,7 @@ class SeistOp(C.Structure):
         ("seed_elem", C.c_uint32), ("seed_path", C.c_uint32), ("seed_alpha", C.c_uint32),
         ("lse", C.c_void_p), ("delta", C.c_void_p),
         ("heads", C.c_int32), ("p_attn", C.c_float), ("seed_attn", C.c_uint32), ("pad0_", C.c_int32),
-        ("zero_bytes", C.c_uint64), ("n_bn", C.c_int32), ("pad1_", C.c_int32),
+        ("zero_bytes", C.c_uint64), ("n_bn", C.c_int32), ("bn_lo", C.c_int32),
     ]
 
 
@@ -57,6 +57,7 @@ CONV_FWD, CONV_BWD_DATA, CONV_BWD_W, RES_BWD = 1, 2, 3, 4
 ATT_FWD, ATT_BWD_Q, ATT_BWD_KV = 5, 6, 7
 HEADVEC_FWD, HEADVEC_BWD = 8, 9
 BN_FINALIZE_FWD, BN_FINALIZE_BWD, ZERO = 10, 11, 12
+BN_PREPARE_FWD, BN_PREPARE_BWD = 13, 14
 
 _lib = None
 

@@ -35,6 +35,7 @@ int launch_att_bwd_kv(const SeistOp& op, cudaStream_t s);
 int launch_headvec_fwd(const SeistOp& op, cudaStream_t s);
 int launch_headvec_bwd(const SeistOp& op, cudaStream_t s);
 int launch_bn_finalize(const SeistOp& op, bool fwd, cudaStream_t s);
+int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s);
 
 static int sm_count() {
   if (g_sm_count == 0) {
@@ -69,6 +70,8 @@ static int run_one(const SeistOp& op, cudaStream_t s) {
     case SEIST_OP_HEADVEC_BWD: return launch_headvec_bwd(op, s);
     case SEIST_OP_BN_FINALIZE_FWD: return launch_bn_finalize(op, true, s);
     case SEIST_OP_BN_FINALIZE_BWD: return launch_bn_finalize(op, false, s);
+    case SEIST_OP_BN_PREPARE_FWD: return launch_bn_prepare(op, true, s);
+    case SEIST_OP_BN_PREPARE_BWD: return launch_bn_prepare(op, false, s);
     case SEIST_OP_ZERO: {
       cudaError_t e = cudaMemsetAsync(op.out.x, 0, op.zero_bytes, s);
       if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }

@@ -150,9 +150,15 @@ __device__ __forceinline__ const float* view_row(const SeistView& v, int n, int 
 __device__ __forceinline__ float* view_grad_row(const SeistView& v, int n, int c) {
   return v.g + ((size_t)n * v.Ct + v.c0 + c) * (size_t)v.L;
 }
+// coefficient table row of channel c of the BN applied by view v (written by the BN_PREPARE ops)
+__device__ __forceinline__ const float* bn_coef_row(const SeistOp& op, int bn, int c) {
+  return op.bn_table[bn].coef + 8 * (size_t)c;
+}
 __device__ __forceinline__ void view_coef(const SeistOp& op, const SeistView& v, int c, float& sc, float& sh) {
   if (v.bn >= 0) {
-    bn_fwd_coef(op.bn_table, v.bn, v.bn_c0 + c, sc, sh);
+    const float2 k = *reinterpret_cast<const float2*>(bn_coef_row(op, v.bn, v.bn_c0 + c));
+    sc = k.x;
+    sh = k.y;
   } else {
     sc = 1.0f;
     sh = 0.0f;
@@ -166,7 +172,10 @@ struct OutGradCoef {
 __device__ __forceinline__ OutGradCoef out_grad_coef(const SeistOp& op, int co) {
   OutGradCoef k;
   if (op.out.bn >= 0 && op.out.g != nullptr) {
-    bn_bwd_coef(op.bn_table, op.out.bn, op.out.bn_c0 + co, k.A, k.Bx, k.Cc);
+    const float4 t = *reinterpret_cast<const float4*>(bn_coef_row(op, op.out.bn, op.out.bn_c0 + co) + 4);
+    k.A = t.x;
+    k.Bx = t.y;
+    k.Cc = t.z;
   } else {
     k.A = 0.f;
     k.Bx = 0.f;
@@ -185,6 +194,13 @@ __device__ __forceinline__ float out_grad_at(const SeistOp& op, const OutGradCoe
     if (op.out_act == SEIST_OUT_SIGMOID) g *= x * (1.0f - x);
   }
   return g;
+}
+
+// khat = (x - mu) * istd of the BN applied by view v
+__device__ __forceinline__ void view_khat(const SeistOp& op, const SeistView& v, int c, float& mu, float& istd) {
+  const float2 k = *reinterpret_cast<const float2*>(bn_coef_row(op, v.bn, v.bn_c0 + c) + 2);
+  mu = k.x;
+  istd = k.y;
 }
 
 // deposit a per-channel pair of gstat partial sums (called by one lane per warp)

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_data_kernel(const __grid_constant
     float sc, sh, mu = 0.f, istd = 0.f;
     view_coef(op, v, cv, sc, sh);
     const bool has_bn = v.bn >= 0;
-    if (has_bn) bn_khat_coef(op.bn_table, v.bn, v.bn_c0 + cv, mu, istd);
+    if (has_bn) view_khat(op, v, cv, mu, istd);
     const float* xr = view_row(v, n, cv);
     float* gr = view_grad_row(v, n, cv);
     const float* drow = d_s + r * TL;
@@ -413,8 +413,9 @@ __global__ void __launch_bounds__(NT) conv_bwd_w_kernel(const __grid_constant__ 
   const int nq = q_hi - q_lo + 1;
   const int TLin = (PC - 1) * stride + k;
   const int TLp = TLin | 1;                  // odd row pitch: lanes on different rows hit different banks
-  float* g_s = smem;                         // [PC][CO_TILE]
-  float* in_s = smem + PC * CO_TILE;         // [ng][nq][TLp]
+  constexpr int GP = CO_TILE + 4;            // row pitch of g_s: spreads the transposed stores over banks
+  float* g_s = smem;                         // [PC][GP]
+  float* in_s = smem + PC * GP;              // [ng][nq][TLp]
   const uint64_t seed = load_seed(op.step_seed);
   const int Lsrc = op.in[0].L;
   const float ratio = op.up_src_L > 0 ? (float)Lsrc / (float)op.L_in : 1.f;
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_w_kernel(const __grid_constant__ 
         const OutGradCoef kc = out_grad_coef(op, co);
         v = out_grad_at(op, kc, n, co, l) * pf * elem_factor(op, seed, n, co, l);
       }
-      g_s[lane * CO_TILE + col] = v;
+      g_s[lane * GP + col] = v;
     }
     // conv-input rows
     const int p_base = l0 * stride - op.pad_left;
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_w_kernel(const __grid_constant__ 
       for (int p = 0; p < PC; ++p) {
         float g[COT];
 #pragma unroll
-        for (int c = 0; c < COT; ++c) g[c] = g_s[p * CO_TILE + row * COT + c];
+        for (int c = 0; c < COT; ++c) g[c] = g_s[p * GP + row * COT + c];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float v = in_s[ioff[j] + p * stride];
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_w_kernel(const __grid_constant__ 
       }
       if (blockIdx.z == 0 && op.dbias != nullptr) {
 #pragma unroll
-        for (int c = 0; c < COT; ++c) bacc[c] += g_s[lane * CO_TILE + row * COT + c];
+        for (int c = 0; c < COT; ++c) bacc[c] += g_s[lane * GP + row * COT + c];
       }
     }
     __syncthreads();
@@ -528,7 +529,7 @@ __global__ void __launch_bounds__(NT) res_bwd_kernel(const __grid_constant__ Sei
     }
     if (v.bn >= 0) {
       float mu, istd;
-      bn_khat_coef(op.bn_table, v.bn, v.bn_c0 + co, mu, istd);
+      view_khat(op, v, co, mu, istd);
       if (ok) {
         const float x = view_row(v, n, co)[l];
         s1 = gv;
@@ -625,7 +626,7 @@ int launch_conv_bwd_w(const SeistOp& op, cudaStream_t s, int sm_count) {
   if (nq_max > gs_in) nq_max = gs_in;
   const int TLin = (PC - 1) * op.stride + op.k;
   const int TLp = TLin | 1;
-  const size_t smem = sizeof(float) * ((size_t)PC * co_tile + (size_t)ng_max * nq_max * TLp);
+  const size_t smem = sizeof(float) * ((size_t)PC * (co_tile + 4) + (size_t)ng_max * nq_max * TLp);
   const int gy = (op.Cout + co_tile - 1) / co_tile, gz = (R + RT - 1) / RT;
   const long tiles = (long)op.N * ((op.L_out + PC - 1) / PC);
   long gx = (4L * sm_count + gy * gz - 1) / (gy * gz);

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) headvec_bwd_kernel(const __grid_constant_
     dm /= (float)v.L;
     float sc, sh, mu = 0.f, istd = 0.f;
     view_coef(op, v, c, sc, sh);
-    if (v.bn >= 0) bn_khat_coef(op.bn_table, v.bn, v.bn_c0 + c, mu, istd);
+    if (v.bn >= 0) view_khat(op, v, c, mu, istd);
     const float* xr = view_row(v, n, c);
     float* gr = view_grad_row(v, n, c);
     float s1 = 0.f, s2 = 0.f;
@@ -169,6 +169,34 @@ __global__ void bn_finalize_bwd_kernel(const SeistBN* tab, int n_bn) {
       // d(beta) of the first BN of a chain is analytically zero
     }
   }
+}
+
+// per-channel coefficient tables (see SeistBN::coef): one block per BN entry of [bn_lo, bn_lo + n)
+__global__ void bn_prepare_fwd_kernel(const SeistBN* tab, int bn_lo) {
+  const int bn = bn_lo + blockIdx.x;
+  const SeistBN& e = tab[bn];
+  if (e.is_chained) return;
+  for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+    float* k = e.coef + 8 * (size_t)c;
+    bn_fwd_coef(tab, bn, c, k[0], k[1]);
+    bn_khat_coef(tab, bn, c, k[2], k[3]);
+  }
+}
+__global__ void bn_prepare_bwd_kernel(const SeistBN* tab, int bn_lo) {
+  const int bn = bn_lo + blockIdx.x;
+  const SeistBN& e = tab[bn];
+  if (e.is_chained) return;
+  for (int c = threadIdx.x; c < e.C; c += blockDim.x) {
+    float* k = e.coef + 8 * (size_t)c;
+    bn_bwd_coef(tab, bn, c, k[4], k[5], k[6]);
+  }
+}
+int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s) {
+  if (op.n_bn <= 0) return 0;
+  if (fwd) bn_prepare_fwd_kernel<<<op.n_bn, 64, 0, s>>>(op.bn_table, op.bn_lo);
+  else bn_prepare_bwd_kernel<<<op.n_bn, 64, 0, s>>>(op.bn_table, op.bn_lo);
+  note_launch();
+  return check_launch("bn_prepare");
 }
 
 int launch_bn_finalize(const SeistOp& op, bool fwd, cudaStream_t s) {

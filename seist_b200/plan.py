@@ -114,6 +114,8 @@ class Op:
     lse: Optional[torch.Tensor] = None
     delta: Optional[torch.Tensor] = None
     zero: Optional[torch.Tensor] = None   # ZERO target
+    bn_lo: int = 0                        # BN_PREPARE: first entry / count
+    n_bn: int = 0
     name: str = ""
     fwd: Optional["Op"] = None            # backward ops point at their forward op
     sync_bn: List[int] = field(default_factory=list)  # BN indices whose (g)stat must be all-reduced BEFORE this op
@@ -482,10 +484,10 @@ class PlanBuilder:
         pl.y_out.need_dxd = True
         if self.training:
             pl.fwd_ops.append(Op(_lib.BN_FINALIZE_FWD, self.N, name="bn_finalize_fwd"))
-        self._mark_sync(pl.fwd_ops, forward=True)
+        pl.fwd_ops = self._insert_prepares(pl.fwd_ops, forward=True)
         if self.need_backward:
             self._emit_backward()
-            self._mark_sync(pl.bwd_ops, forward=False)
+            pl.bwd_ops = self._insert_prepares(pl.bwd_ops, forward=False)
         return pl
 
     # ---- backward --------------------------------------------------------------------------------
@@ -535,39 +537,38 @@ class PlanBuilder:
                 pass
         ops.append(Op(_lib.BN_FINALIZE_BWD, self.N, name="bn_finalize_bwd"))
 
-    def _mark_sync(self, ops: List[Op], forward: bool):
-        """Data-parallel SyncBatchNorm (reference training/train.py:374): the (g)stat slots of a BN must
-        be summed over ranks after its last producer and before its first consumer."""
-        if self.world <= 1:
-            return
-        pending: Dict[int, bool] = {}
+    def _insert_prepares(self, ops: List[Op], forward: bool) -> List[Op]:
+        """Insert the BN_PREPARE ops: the per-channel coefficient table of a BN is computed once, after its
+        last producer and before its first consumer (forward: scale/shift/khat from the batch statistics;
+        backward: A/Bx/Cc from gstat).  Under data parallelism that is also the point where the (g)stat
+        slots are summed over ranks (reference training/train.py:374, SyncBatchNorm)."""
+        kind = _lib.BN_PREPARE_FWD if forward else _lib.BN_PREPARE_BWD
+        nb = len(self.plan.bns)
+        if forward and not self.training:
+            return [Op(kind, self.N, bn_lo=0, n_bn=nb, name="bn_prepare_all")] + ops
+        out: List[Op] = []
+        ready = set()
         for op in ops:
             needs = set()
             if forward:
-                for v in op.ins + [r for r in (op.res_a, op.res_b) if r is not None]:
+                for v in list(op.ins) + [op.res_a, op.res_b]:
                     if v is not None and v.buf is not None and v.bn >= 0:
                         needs.add(v.bn)
-                if op.kind == _lib.BN_FINALIZE_FWD:
-                    needs.update(pending)
-            else:
-                if op.out is not None and op.out.bn >= 0 and op.kind in (
-                        _lib.CONV_BWD_DATA, _lib.CONV_BWD_W, _lib.RES_BWD):
-                    needs.add(op.out.bn)
-                if op.kind == _lib.BN_FINALIZE_BWD:
-                    needs.update(pending)
-            op.sync_bn = sorted(b for b in needs if pending.get(b, False))
-            for b in op.sync_bn:
-                pending[b] = False
-            # producers
-            if forward:
-                if op.kind == _lib.CONV_FWD and op.out.bn >= 0:
-                    pending[op.out.bn] = True
-            else:
-                tg = list(op.ins) + [r for r in (op.res_a, op.res_b) if r is not None]
-                if op.kind in (_lib.CONV_BWD_DATA, _lib.RES_BWD):
-                    for v in tg:
-                        if v is not None and v.buf is not None and v.bn >= 0:
-                            pending[v.bn] = True
+            elif op.kind in (_lib.CONV_BWD_DATA, _lib.CONV_BWD_W, _lib.RES_BWD) and op.out.bn >= 0 \
+                    and op.out.buf.need_du:
+                needs.add(op.out.bn)
+            todo = sorted(b for b in needs if b not in ready)
+            run: List[int] = []
+            for b in todo + [None]:
+                if run and (b is None or b != run[-1] + 1):
+                    out.append(Op(kind, self.N, bn_lo=run[0], n_bn=len(run), name=f"bn_prepare[{run[0]}:{run[-1] + 1}]",
+                                  sync_bn=list(run) if self.world > 1 else []))
+                    run = []
+                if b is not None:
+                    run.append(b)
+            ready.update(todo)
+            out.append(op)
+        return out
 
 
 # =================================================================================================
@@ -610,6 +611,7 @@ def allocate(plan: Plan, with_backward: bool):
     nst = max(sum(2 * e.C for e in plan.bns), 2)
     plan.stat = torch.zeros(nst, dtype=torch.float64, device=dev)
     plan.gstat = torch.zeros(nst, dtype=torch.float64, device=dev)
+    plan.coef = torch.zeros(4 * nst, dtype=torch.float32, device=dev)   # [C][8] per BN entry
     plan.step_seed = torch.zeros(1, dtype=torch.int64, device=dev)
 
 
@@ -630,6 +632,7 @@ def bn_table_struct(plan: Plan):
         s.gstat = plan.gstat.data_ptr() + 8 * e.st_off
         s.dgamma = flat.G.data_ptr() + 4 * e.gamma.off
         s.dbeta = flat.G.data_ptr() + 4 * e.beta.off
+        s.coef = plan.coef.data_ptr() + 4 * (4 * e.st_off)
         s.count = e.count
         s.C = e.C
         s.chain = e.chain
@@ -703,6 +706,8 @@ def to_c(plan: Plan, ops: List[Op]):
         c.lse = _ptr(f.lse)
         c.delta = _ptr(f.delta)
         c.n_bn = len(plan.bns)
+        if op.kind in (_lib.BN_PREPARE_FWD, _lib.BN_PREPARE_BWD):
+            c.n_bn, c.bn_lo = op.n_bn, op.bn_lo
     return arr
 
 
