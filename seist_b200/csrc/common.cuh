@@ -210,4 +210,18 @@ __device__ __forceinline__ void gstat_add(const SeistOp& op, const SeistView& v,
   atomicAdd(&e.gstat[e.C + v.bn_c0 + c], (double)s2);
 }
 
+// drop factors of the epilogue: fac = delta(n) * D(n,co,l), alpha(n)
+__device__ __forceinline__ float path_factor(const SeistOp& op, uint64_t seed, int n) {
+  return op.p_path > 0.f ? keep_scale(op.p_path, seed, op.seed_path, (uint64_t)n) : 1.f;
+}
+__device__ __forceinline__ float alpha_factor(const SeistOp& op, uint64_t seed, int n) {
+  return op.p_alpha > 0.f ? keep_scale(op.p_alpha, seed, op.seed_alpha, (uint64_t)n) : 1.f;
+}
+__device__ __forceinline__ float elem_factor(const SeistOp& op, uint64_t seed, int n, int co, int l) {
+  if (op.p_elem <= 0.f) return 1.f;
+  const uint64_t idx = ((uint64_t)n * op.Cout + co) * (uint64_t)op.L_out + l;
+  return keep_scale(op.p_elem, seed, op.seed_elem, idx);
+}
+
+
 }  // namespace seist

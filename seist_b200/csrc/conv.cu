@@ -73,17 +73,50 @@ __device__ __forceinline__ RowSrc make_row(const SeistOp& op, int n, int ci) {
   return r;
 }
 
-// drop factors of the epilogue: fac = delta(n) * D(n,co,l), alpha(n)
-__device__ __forceinline__ float path_factor(const SeistOp& op, uint64_t seed, int n) {
-  return op.p_path > 0.f ? keep_scale(op.p_path, seed, op.seed_path, (uint64_t)n) : 1.f;
-}
-__device__ __forceinline__ float alpha_factor(const SeistOp& op, uint64_t seed, int n) {
-  return op.p_alpha > 0.f ? keep_scale(op.p_alpha, seed, op.seed_alpha, (uint64_t)n) : 1.f;
-}
-__device__ __forceinline__ float elem_factor(const SeistOp& op, uint64_t seed, int n, int co, int l) {
-  if (op.p_elem <= 0.f) return 1.f;
-  const uint64_t idx = ((uint64_t)n * op.Cout + co) * (uint64_t)op.L_out + l;
-  return keep_scale(op.p_elem, seed, op.seed_elem, idx);
+
+// Stage `nrows` conv-input rows of `width` samples into shared memory (row r at dst + r*pitch).  A warp
+// keeps four rows in flight per pass so four independent global loads are outstanding per lane.
+template <typename ChanFn>
+__device__ __forceinline__ void stage_rows(const SeistOp& op, int n, float* dst, int pitch, int width, int nrows,
+                                           int p_base, int Lsrc, float ratio, ChanFn&& chan_of) {
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  const bool plain = op.pool <= 1 && op.up_src_L == 0;
+  for (int r0 = row; r0 < nrows; r0 += 4 * ROWS) {
+    RowSrc rs[4];
+    bool valid[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * ROWS;
+      valid[u] = false;
+      int ci = 0;
+      if (r < nrows) ci = chan_of(r, valid[u]);
+      rs[u] = make_row(op, n, valid[u] ? ci : 0);
+    }
+    for (int pos = lane; pos < width; pos += 32) {
+      const int p = p_base + pos;
+      float v[4];
+      if (plain) {
+        const bool inb = p >= 0 && p < op.L_in;
+        const int pc = inb ? p : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = rs[u].x[pc];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float t = fmaf(rs[u].sc, v[u], rs[u].sh);
+          if (rs[u].act == SEIST_ACT_GELU) t = gelu_f(t);
+          v[u] = (inb && valid[u]) ? t : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = valid[u] ? conv_input_at(op, rs[u], p, Lsrc, ratio) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * ROWS;
+        if (r < nrows) dst[r * pitch + pos] = v[u];
+      }
+    }
+  }
 }
 
 // ================================================================================================
@@ -121,16 +154,11 @@ __global__ void __launch_bounds__(NT) conv_fwd_kernel(const __grid_constant__ Se
   const int p_base = l0 * stride - op.pad_left;
   for (int q0 = 0; q0 < gs_in; q0 += qc) {
     // ---- stage the input tile: one warp per channel row, lanes along samples -------------------
-    for (int r = row; r < ng * qc; r += ROWS) {
+    stage_rows(op, n, in_s, TLin, TLin, ng * qc, p_base, Lsrc, ratio, [&](int r, bool& valid) {
       const int g = r / qc, qq = r - g * qc;
-      float* dst = in_s + r * TLin;
-      if (q0 + qq < gs_in) {
-        const RowSrc rs = make_row(op, n, (g_lo + g) * gs_in + q0 + qq);
-        for (int pos = lane; pos < TLin; pos += 32) dst[pos] = conv_input_at(op, rs, p_base + pos, Lsrc, ratio);
-      } else {
-        for (int pos = lane; pos < TLin; pos += 32) dst[pos] = 0.f;
-      }
-    }
+      valid = q0 + qq < gs_in;
+      return (g_lo + g) * gs_in + q0 + qq;
+    });
     // ---- stage weights k-major: w_s[(qq*k + t)*CO_TILE + col] ----------------------------------
     for (int idx = threadIdx.x; idx < qc * k * CO_TILE; idx += NT) {
       const int col = idx % CO_TILE;
@@ -249,24 +277,32 @@ __global__ void __launch_bounds__(NT) conv_bwd_data_kernel(const __grid_constant
 
   const int m_base = p0 + op.pad_left - (k - 1);
   for (int o0 = 0; o0 < gs_out; o0 += oc) {
-    for (int r = row; r < ng * oc; r += ROWS) {
-      const int g = r / oc, oo = r - g * oc;
-      float* dst = z_s + r * TLz;
-      if (o0 + oo < gs_out) {
-        const int co = (g_lo + g) * gs_out + o0 + oo;
-        const OutGradCoef kc = out_grad_coef(op, co);
-        for (int pos = lane; pos < TLz; pos += 32) {
-          const int m = m_base + pos;
-          float v = 0.f;
-          if (m >= 0) {
-            const int l = m / stride;
-            if (l * stride == m && l < op.L_out)
-              v = out_grad_at(op, kc, n, co, l) * pf * elem_factor(op, seed, n, co, l);
+    for (int r0 = row; r0 < ng * oc; r0 += 4 * ROWS) {
+      OutGradCoef kc[4];
+      int cos[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * ROWS;
+        const int g = r / oc, oo = r - g * oc;
+        cos[u] = (r < ng * oc && o0 + oo < gs_out) ? (g_lo + g) * gs_out + o0 + oo : -1;
+        kc[u] = out_grad_coef(op, cos[u] >= 0 ? cos[u] : 0);
+      }
+      for (int pos = lane; pos < TLz; pos += 32) {
+        const int m = m_base + pos;
+        const int l = m >= 0 ? m / stride : 0;
+        const bool inb = m >= 0 && l * stride == m && l < op.L_out;
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (inb && cos[u] >= 0) ? out_grad_at(op, kc[u], n, cos[u], l) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * ROWS;
+          if (r < ng * oc) {
+            float t = v[u] * pf;
+            if (op.p_elem > 0.f && inb && cos[u] >= 0) t *= elem_factor(op, seed, n, cos[u], l);
+            z_s[r * TLz + pos] = t;
           }
-          dst[pos] = v;
         }
-      } else {
-        for (int pos = lane; pos < TLz; pos += 32) dst[pos] = 0.f;
       }
     }
     // flipped, transposed weights: w_s[(oo*k + tf)*CI_TILE + col] = W[co][q][k-1-tf]
@@ -448,24 +484,35 @@ __global__ void __launch_bounds__(NT) conv_bwd_w_kernel(const __grid_constant__ 
     const int l0 = (tile - n * chunks_per_n) * PC;
     const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
     // gacc tile, transposed: g_s[p][col]
-    for (int col = row; col < CO_TILE; col += ROWS) {
-      const int co = co_base + col;
-      float v = 0.f;
+    for (int c0 = row; c0 < CO_TILE; c0 += 4 * ROWS) {
       const int l = l0 + lane;   // PC == 32
-      if (co < op.Cout && l < op.L_out) {
-        const OutGradCoef kc = out_grad_coef(op, co);
-        v = out_grad_at(op, kc, n, co, l) * pf * elem_factor(op, seed, n, co, l);
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int co = co_base + c0 + u * ROWS;
+        v[u] = 0.f;
+        if (c0 + u * ROWS < CO_TILE && co < op.Cout && l < op.L_out) {
+          const OutGradCoef kc = out_grad_coef(op, co);
+          v[u] = out_grad_at(op, kc, n, co, l);
+        }
       }
-      g_s[lane * GP + col] = v;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int col = c0 + u * ROWS, co = co_base + col;
+        if (col < CO_TILE) {
+          float t = v[u] * pf;
+          if (op.p_elem > 0.f && co < op.Cout && l < op.L_out) t *= elem_factor(op, seed, n, co, l);
+          g_s[lane * GP + col] = t;
+        }
+      }
     }
     // conv-input rows
     const int p_base = l0 * stride - op.pad_left;
-    for (int r = row; r < ng * nq; r += ROWS) {
+    stage_rows(op, n, in_s, TLp, TLin, ng * nq, p_base, Lsrc, ratio, [&](int r, bool& valid) {
       const int g = r / nq, qq = r - g * nq;
-      const RowSrc rs = make_row(op, n, (g_lo + g) * gs_in + q_lo + qq);
-      float* dst = in_s + r * TLp;
-      for (int pos = lane; pos < TLin; pos += 32) dst[pos] = conv_input_at(op, rs, p_base + pos, Lsrc, ratio);
-    }
+      valid = true;
+      return (g_lo + g) * gs_in + q_lo + qq;
+    });
     __syncthreads();
     if (co0 < op.Cout) {
       for (int p = 0; p < PC; ++p) {

@@ -1,0 +1,530 @@
+// Pointwise (k = 1, stride 1, groups 1) convolutions — the bulk of the encoder FLOPs and bytes
+// (reference models/seist.py:86,107,111,130,142,182,225,287,351-364,429,451).
+//
+// Streaming design: a thread owns one quad of 4 consecutive samples and a tile of output channels; it
+// walks the reduction channels 8 at a time, issuing eight independent 16-byte global loads before any
+// use (memory-level parallelism instead of a staged tile), applies BatchNorm/GELU of the consumer view in
+// registers and accumulates against weights held k-major in shared memory (one broadcast vector per
+// reduction channel).  A CTA runs G quads per thread back to back so the BatchNorm statistics of the
+// result are carried in registers and reduced (shuffles -> shared -> one double atomic per channel) once.
+#include "common.cuh"
+
+namespace seist {
+
+constexpr int PW_NT = 128;
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+struct PwChan {          // one reduction / target channel, resolved once per CTA
+  const float* x;        // row base for n = 0
+  float* g;              // gradient row base for n = 0 (backward targets) or nullptr
+  long long nstride;     // elements between consecutive waveforms
+  float sc, sh, mu, istd;
+  int act, bn, bnc, accum;
+};
+
+__device__ __forceinline__ PwChan make_chan(const SeistOp& op, int ci, bool want_khat) {
+  int cv;
+  const int vi = resolve_view(op, ci, cv);
+  const SeistView& v = op.in[vi];
+  PwChan c;
+  c.x = v.x + (size_t)(v.c0 + cv) * v.L;
+  c.g = v.g ? v.g + (size_t)(v.c0 + cv) * v.L : nullptr;
+  c.nstride = (long long)v.Ct * v.L;
+  view_coef(op, v, cv, c.sc, c.sh);
+  c.mu = 0.f;
+  c.istd = 0.f;
+  if (want_khat && v.bn >= 0) view_khat(op, v, cv, c.mu, c.istd);
+  c.act = v.act;
+  c.bn = v.bn;
+  c.bnc = v.bn_c0 + cv;
+  c.accum = v.accum;
+  return c;
+}
+
+__device__ __forceinline__ float4 apply_view(float4 v, float sc, float sh, int act) {
+  v.x = fmaf(sc, v.x, sh);
+  v.y = fmaf(sc, v.y, sh);
+  v.z = fmaf(sc, v.z, sh);
+  v.w = fmaf(sc, v.w, sh);
+  if (act == SEIST_ACT_GELU) {
+    v.x = gelu_f(v.x);
+    v.y = gelu_f(v.y);
+    v.z = gelu_f(v.z);
+    v.w = gelu_f(v.w);
+  }
+  return v;
+}
+
+// CTA-wide reduction of per-thread partial sums part[NV] -> double atomics.  red_s: [4][NV] floats.
+template <int NV, typename F>
+__device__ __forceinline__ void cta_reduce_atomic(float (&part)[NV], float* red_s, F&& sink) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float s = warp_sum(part[i]);
+    if (lane == 0) red_s[warp * NV + i] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV; i += PW_NT) {
+    const float s = red_s[i] + red_s[NV + i] + red_s[2 * NV + i] + red_s[3 * NV + i];
+    sink(i, s);
+  }
+}
+
+// ================================================================================================
+// forward: out[co] = alpha * [ drop( sum_ci W[co][ci] f(in[ci]) + b ) + res_a ] + res_b
+// grid (ceil(N*L/4 / (128*G)), ceil(Cout/COUT_T))
+// ================================================================================================
+template <int COUT_T>
+__global__ void __launch_bounds__(PW_NT) pw_fwd_kernel(const __grid_constant__ SeistOp op, const int G) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int Cin = op.Cin, Cin8 = (Cin + 7) & ~7;
+  PwChan* ch_s = reinterpret_cast<PwChan*>(sm_raw);                       // [Cin8]
+  float* w_s = reinterpret_cast<float*>(ch_s + Cin8);                     // [Cin8][COUT_T]
+  float* ep_s = w_s + Cin8 * COUT_T;                                      // bias, ra_sc, ra_sh, rb_sc, rb_sh [COUT_T] each
+  float* red_s = ep_s + 5 * COUT_T;                                       // [4][2*COUT_T]
+  const int tid = threadIdx.x;
+  const int co_base = blockIdx.y * COUT_T;
+  const int L = op.L_out, LQ = L >> 2;
+
+  for (int ci = tid; ci < Cin8; ci += PW_NT) {
+    if (ci < Cin) {
+      ch_s[ci] = make_chan(op, ci, false);
+    } else {
+      PwChan z = make_chan(op, 0, false);
+      z.act = 0;
+      ch_s[ci] = z;   // padded channel: valid address, zero weights
+    }
+  }
+  for (int idx = tid; idx < Cin8 * COUT_T; idx += PW_NT) {
+    const int ci = idx / COUT_T, col = idx - ci * COUT_T;
+    const int co = co_base + col;
+    w_s[idx] = (co < op.Cout && ci < Cin) ? op.W[(size_t)co * Cin + ci] : 0.f;
+  }
+  for (int col = tid; col < COUT_T; col += PW_NT) {
+    const int co = co_base + col;
+    float b = 0.f, asc = 1.f, ash = 0.f, bsc = 1.f, bsh = 0.f;
+    if (co < op.Cout) {
+      if (op.bias) b = op.bias[co];
+      if (op.res_a.C > 0) view_coef(op, op.res_a, co, asc, ash);
+      if (op.res_b.C > 0) view_coef(op, op.res_b, co, bsc, bsh);
+    }
+    ep_s[col] = b;
+    ep_s[COUT_T + col] = asc;
+    ep_s[2 * COUT_T + col] = ash;
+    ep_s[3 * COUT_T + col] = bsc;
+    ep_s[4 * COUT_T + col] = bsh;
+  }
+  __syncthreads();
+
+  const uint64_t seed = load_seed(op.step_seed);
+  const long long NQ = (long long)op.N * LQ;
+  const bool stats = (op.out.bn >= 0) && op.bn_table[op.out.bn >= 0 ? op.out.bn : 0].use_batch;
+  float st[2 * COUT_T];
+#pragma unroll
+  for (int i = 0; i < 2 * COUT_T; ++i) st[i] = 0.f;
+
+  for (int g = 0; g < G; ++g) {
+    const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
+    const bool ok = f < NQ;
+    const int n = ok ? (int)(f / LQ) : 0;
+    const int l = ok ? (int)(f - (long long)n * LQ) * 4 : 0;
+    float4 acc[COUT_T];
+#pragma unroll
+    for (int c = 0; c < COUT_T; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ci0 = 0; ci0 < Cin8; ci0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const PwChan& c = ch_s[ci0 + j];
+        v[j] = ldg4(c.x + (long long)n * c.nstride + l);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const PwChan& c = ch_s[ci0 + j];
+        const float4 u = apply_view(v[j], c.sc, c.sh, c.act);
+        const float* wr = w_s + (ci0 + j) * COUT_T;
+#pragma unroll
+        for (int co = 0; co < COUT_T; ++co) {
+          const float w = wr[co];
+          acc[co].x = fmaf(w, u.x, acc[co].x);
+          acc[co].y = fmaf(w, u.y, acc[co].y);
+          acc[co].z = fmaf(w, u.z, acc[co].z);
+          acc[co].w = fmaf(w, u.w, acc[co].w);
+        }
+      }
+    }
+    if (!ok) continue;
+    const float pf = path_factor(op, seed, n), af = alpha_factor(op, seed, n);
+#pragma unroll
+    for (int col = 0; col < COUT_T; ++col) {
+      const int co = co_base + col;
+      if (co >= op.Cout) break;
+      float4 r = acc[col];
+      const float b = ep_s[col];
+      r.x = (r.x + b) * pf;
+      r.y = (r.y + b) * pf;
+      r.z = (r.z + b) * pf;
+      r.w = (r.w + b) * pf;
+      if (op.p_elem > 0.f) {
+        const uint64_t idx = ((uint64_t)n * op.Cout + co) * (uint64_t)L + l;
+        r.x *= keep_scale(op.p_elem, seed, op.seed_elem, idx);
+        r.y *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 1);
+        r.z *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 2);
+        r.w *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 3);
+      }
+      if (op.res_a.C > 0) {
+        const float4 a = ldg4(op.res_a.x + ((size_t)n * op.res_a.Ct + op.res_a.c0 + co) * (size_t)L + l);
+        const float sc = ep_s[COUT_T + col], sh = ep_s[2 * COUT_T + col];
+        r.x += fmaf(sc, a.x, sh);
+        r.y += fmaf(sc, a.y, sh);
+        r.z += fmaf(sc, a.z, sh);
+        r.w += fmaf(sc, a.w, sh);
+      }
+      r.x *= af;
+      r.y *= af;
+      r.z *= af;
+      r.w *= af;
+      if (op.res_b.C > 0) {
+        const float4 a = ldg4(op.res_b.x + ((size_t)n * op.res_b.Ct + op.res_b.c0 + co) * (size_t)L + l);
+        const float sc = ep_s[3 * COUT_T + col], sh = ep_s[4 * COUT_T + col];
+        r.x += fmaf(sc, a.x, sh);
+        r.y += fmaf(sc, a.y, sh);
+        r.z += fmaf(sc, a.z, sh);
+        r.w += fmaf(sc, a.w, sh);
+      }
+      if (op.out_act == SEIST_OUT_SIGMOID) {
+        r.x = sigmoid_f(r.x);
+        r.y = sigmoid_f(r.y);
+        r.z = sigmoid_f(r.z);
+        r.w = sigmoid_f(r.w);
+      }
+      st4(op.out.x + ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l, r);
+      st[2 * col] += (r.x + r.y) + (r.z + r.w);
+      st[2 * col + 1] += fmaf(r.x, r.x, r.y * r.y) + fmaf(r.z, r.z, r.w * r.w);
+    }
+  }
+  if (stats) {
+    cta_reduce_atomic<2 * COUT_T>(st, red_s, [&](int i, float s) {
+      const int co = co_base + (i >> 1);
+      if (co < op.Cout) {
+        const SeistBN& e = op.bn_table[op.out.bn];
+        atomicAdd(&e.stat[(i & 1) * e.C + op.out.bn_c0 + co], (double)s);
+      }
+    });
+  }
+}
+
+// ================================================================================================
+// backward (data): d in[ci] = sum_co W[co][ci] gacc[co];  gacc = dOut * alpha * delta * D
+// dOut = A*du + Bx*x + Cc + dxd (then sigmoid').  grid (ceil(NQ/(128*G)), ceil(Cin/CI_T))
+// ================================================================================================
+struct PwOut {   // per output channel of the forward op, resolved once per CTA
+  float A, Bx, Cc;
+};
+
+template <int CI_T>
+__global__ void __launch_bounds__(PW_NT) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int Cout = op.Cout, Cout4 = (Cout + 3) & ~3, Cin = op.Cin;
+  PwChan* ch_s = reinterpret_cast<PwChan*>(sm_raw);                       // [CI_T] targets
+  PwOut* oc_s = reinterpret_cast<PwOut*>(ch_s + CI_T);                    // [Cout4]
+  float* w_s = reinterpret_cast<float*>(oc_s + Cout4);                    // [Cout4][CI_T]
+  float* red_s = w_s + Cout4 * CI_T;                                      // [4][2*CI_T]
+  const int tid = threadIdx.x;
+  const int ci_base = blockIdx.y * CI_T;
+  const int L = op.L_out, LQ = L >> 2;
+
+  for (int col = tid; col < CI_T; col += PW_NT) {
+    const int ci = ci_base + col;
+    PwChan c = make_chan(op, ci < Cin ? ci : 0, true);
+    if (ci >= Cin) c.g = nullptr;
+    ch_s[col] = c;
+  }
+  for (int co = tid; co < Cout4; co += PW_NT) {
+    PwOut o = {0.f, 0.f, 0.f};
+    if (co < Cout) {
+      const OutGradCoef k = out_grad_coef(op, co);
+      o.A = k.A;
+      o.Bx = k.Bx;
+      o.Cc = k.Cc;
+    }
+    oc_s[co] = o;
+  }
+  for (int idx = tid; idx < Cout4 * CI_T; idx += PW_NT) {
+    const int co = idx / CI_T, col = idx - co * CI_T;
+    const int ci = ci_base + col;
+    w_s[idx] = (co < Cout && ci < Cin) ? op.W[(size_t)co * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+
+  const uint64_t seed = load_seed(op.step_seed);
+  const long long NQ = (long long)op.N * LQ;
+  const bool has_bn = (op.out.bn >= 0 && op.out.g != nullptr);
+  const bool need_x = has_bn || op.out_act == SEIST_OUT_SIGMOID;
+  float st[2 * CI_T];
+#pragma unroll
+  for (int i = 0; i < 2 * CI_T; ++i) st[i] = 0.f;
+
+  for (int g = 0; g < G; ++g) {
+    const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
+    const bool ok = f < NQ;
+    const int n = ok ? (int)(f / LQ) : 0;
+    const int l = ok ? (int)(f - (long long)n * LQ) * 4 : 0;
+    const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
+    float4 acc[CI_T];
+#pragma unroll
+    for (int c = 0; c < CI_T; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t obase = ((size_t)n * op.out.Ct + op.out.c0) * (size_t)L + l;
+    for (int co0 = 0; co0 < Cout4; co0 += 4) {
+      float4 dx[4], du[4], xo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = min(co0 + j, Cout - 1);
+        const size_t off = obase + (size_t)co * L;
+        dx[j] = op.out_dxd ? ldg4(op.out_dxd + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        du[j] = has_bn ? ldg4(op.out.g + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xo[j] = need_x ? ldg4(op.out.x + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int co = co0 + j;
+        const PwOut o = oc_s[co];
+        float4 gv;
+        gv.x = dx[j].x + fmaf(o.A, du[j].x, fmaf(o.Bx, xo[j].x, o.Cc));
+        gv.y = dx[j].y + fmaf(o.A, du[j].y, fmaf(o.Bx, xo[j].y, o.Cc));
+        gv.z = dx[j].z + fmaf(o.A, du[j].z, fmaf(o.Bx, xo[j].z, o.Cc));
+        gv.w = dx[j].w + fmaf(o.A, du[j].w, fmaf(o.Bx, xo[j].w, o.Cc));
+        if (op.out_act == SEIST_OUT_SIGMOID) {
+          gv.x *= xo[j].x * (1.f - xo[j].x);
+          gv.y *= xo[j].y * (1.f - xo[j].y);
+          gv.z *= xo[j].z * (1.f - xo[j].z);
+          gv.w *= xo[j].w * (1.f - xo[j].w);
+        }
+        gv.x *= pf;
+        gv.y *= pf;
+        gv.z *= pf;
+        gv.w *= pf;
+        if (op.p_elem > 0.f) {
+          const uint64_t idx = ((uint64_t)n * Cout + min(co, Cout - 1)) * (uint64_t)L + l;
+          gv.x *= keep_scale(op.p_elem, seed, op.seed_elem, idx);
+          gv.y *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 1);
+          gv.z *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 2);
+          gv.w *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 3);
+        }
+        const float* wr = w_s + co * CI_T;   // zero rows for co >= Cout
+#pragma unroll
+        for (int c = 0; c < CI_T; ++c) {
+          const float w = wr[c];
+          acc[c].x = fmaf(w, gv.x, acc[c].x);
+          acc[c].y = fmaf(w, gv.y, acc[c].y);
+          acc[c].z = fmaf(w, gv.z, acc[c].z);
+          acc[c].w = fmaf(w, gv.w, acc[c].w);
+        }
+      }
+    }
+    if (!ok) continue;
+#pragma unroll
+    for (int col = 0; col < CI_T; ++col) {
+      const PwChan& c = ch_s[col];
+      if (c.g == nullptr) continue;
+      float4 gg = acc[col];
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      const long long off = (long long)n * c.nstride + l;
+      if (c.act == SEIST_ACT_GELU || c.bn >= 0) x = ldg4(c.x + off);
+      if (c.act == SEIST_ACT_GELU) {
+        gg.x *= gelu_grad_f(fmaf(c.sc, x.x, c.sh));
+        gg.y *= gelu_grad_f(fmaf(c.sc, x.y, c.sh));
+        gg.z *= gelu_grad_f(fmaf(c.sc, x.z, c.sh));
+        gg.w *= gelu_grad_f(fmaf(c.sc, x.w, c.sh));
+      }
+      if (c.bn >= 0) {
+        st[2 * col] += (gg.x + gg.y) + (gg.z + gg.w);
+        st[2 * col + 1] += fmaf(gg.x, (x.x - c.mu) * c.istd, gg.y * ((x.y - c.mu) * c.istd)) +
+                           fmaf(gg.z, (x.z - c.mu) * c.istd, gg.w * ((x.w - c.mu) * c.istd));
+      }
+      float* gp = c.g + off;
+      if (c.accum) {
+        const float4 old = ld4(gp);
+        gg.x += old.x;
+        gg.y += old.y;
+        gg.z += old.z;
+        gg.w += old.w;
+      }
+      st4(gp, gg);
+    }
+  }
+  cta_reduce_atomic<2 * CI_T>(st, red_s, [&](int i, float s) {
+    const PwChan& c = ch_s[i >> 1];
+    if (c.g != nullptr && c.bn >= 0) {
+      const SeistBN& e = op.bn_table[c.bn];
+      atomicAdd(&e.gstat[(i & 1) * e.C + c.bnc], (double)s);
+    }
+  });
+}
+
+// ================================================================================================
+// backward: residual pass-through, vectorised.  grid (ceil(NQ/(128*G)), Cout): one channel per CTA.
+// ================================================================================================
+__global__ void __launch_bounds__(PW_NT) res_bwd4_kernel(const __grid_constant__ SeistOp op, const int G) {
+  __shared__ float red_s[4 * 4];
+  const int tid = threadIdx.x;
+  const int co = blockIdx.y;
+  const int L = op.L_out, LQ = L >> 2;
+  const long long NQ = (long long)op.N * LQ;
+  const uint64_t seed = load_seed(op.step_seed);
+  const OutGradCoef kc = out_grad_coef(op, co);
+  const bool has_bn = (op.out.bn >= 0 && op.out.g != nullptr);
+  const bool need_x = has_bn || op.out_act == SEIST_OUT_SIGMOID;
+  const SeistView& va = op.res_a;
+  const SeistView& vb = op.res_b;
+  const bool wa = va.C > 0 && va.g != nullptr, wb = vb.C > 0 && vb.g != nullptr;
+  float amu = 0.f, aistd = 0.f, bmu = 0.f, bistd = 0.f;
+  if (wa && va.bn >= 0) view_khat(op, va, co, amu, aistd);
+  if (wb && vb.bn >= 0) view_khat(op, vb, co, bmu, bistd);
+  float st[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int g = 0; g < G; ++g) {
+    const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
+    if (f >= NQ) break;
+    const int n = (int)(f / LQ);
+    const int l = (int)(f - (long long)n * LQ) * 4;
+    const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l;
+    float4 gv = op.out_dxd ? ldg4(op.out_dxd + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (need_x) {
+      const float4 x = ldg4(op.out.x + off);
+      if (has_bn) {
+        const float4 du = ldg4(op.out.g + off);
+        gv.x += fmaf(kc.A, du.x, fmaf(kc.Bx, x.x, kc.Cc));
+        gv.y += fmaf(kc.A, du.y, fmaf(kc.Bx, x.y, kc.Cc));
+        gv.z += fmaf(kc.A, du.z, fmaf(kc.Bx, x.z, kc.Cc));
+        gv.w += fmaf(kc.A, du.w, fmaf(kc.Bx, x.w, kc.Cc));
+      }
+      if (op.out_act == SEIST_OUT_SIGMOID) {
+        gv.x *= x.x * (1.f - x.x);
+        gv.y *= x.y * (1.f - x.y);
+        gv.z *= x.z * (1.f - x.z);
+        gv.w *= x.w * (1.f - x.w);
+      }
+    }
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const SeistView& v = which == 0 ? va : vb;
+      if (!(which == 0 ? wa : wb)) continue;
+      float4 gg = gv;
+      if (which == 0) {
+        const float af = alpha_factor(op, seed, n);
+        gg.x *= af;
+        gg.y *= af;
+        gg.z *= af;
+        gg.w *= af;
+      }
+      const size_t voff = ((size_t)n * v.Ct + v.c0 + co) * (size_t)L + l;
+      if (v.bn >= 0) {
+        const float4 x = ldg4(v.x + voff);
+        const float mu = which == 0 ? amu : bmu, is = which == 0 ? aistd : bistd;
+        st[2 * which] += (gg.x + gg.y) + (gg.z + gg.w);
+        st[2 * which + 1] += fmaf(gg.x, (x.x - mu) * is, gg.y * ((x.y - mu) * is)) +
+                             fmaf(gg.z, (x.z - mu) * is, gg.w * ((x.w - mu) * is));
+      }
+      float* gp = v.g + voff;
+      if (v.accum) {
+        const float4 old = ld4(gp);
+        gg.x += old.x;
+        gg.y += old.y;
+        gg.z += old.z;
+        gg.w += old.w;
+      }
+      st4(gp, gg);
+    }
+  }
+  cta_reduce_atomic<4>(st, red_s, [&](int i, float s) {
+    const SeistView& v = (i >> 1) == 0 ? va : vb;
+    const bool w = (i >> 1) == 0 ? wa : wb;
+    if (w && v.bn >= 0) {
+      const SeistBN& e = op.bn_table[v.bn];
+      atomicAdd(&e.gstat[(i & 1) * e.C + v.bn_c0 + co], (double)s);
+    }
+  });
+}
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+bool pw_eligible(const SeistOp& op) {
+  if (op.k != 1 || op.stride != 1 || op.groups != 1 || op.pool > 1 || op.up_src_L > 0) return false;
+  if (op.L_out & 3) return false;
+  return true;
+}
+
+static int pick_G(long long nq, int tiles_y, int sm_count) {
+  // enough CTAs for ~4 waves, but several quads per thread to amortise the per-CTA setup / reduction
+  long long ctas = (nq + PW_NT - 1) / PW_NT;
+  int G = 1;
+  while (G < 8 && (ctas / (2 * G)) * tiles_y >= 4LL * sm_count) G *= 2;
+  return G;
+}
+
+template <typename K>
+static int pw_set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+int launch_pw_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
+  const int cot = op.Cout > 8 ? 16 : 8;
+  const int Cin8 = (op.Cin + 7) & ~7;
+  const size_t smem = sizeof(PwChan) * Cin8 + sizeof(float) * ((size_t)Cin8 * cot + 5 * cot + 4 * 2 * cot);
+  const long long nq = (long long)op.N * (op.L_out >> 2);
+  const int ty = (op.Cout + cot - 1) / cot;
+  const int G = pick_G(nq, ty, sm_count);
+  dim3 grid((unsigned)((nq + (long long)PW_NT * G - 1) / ((long long)PW_NT * G)), ty);
+  int rc = 0;
+  if (cot == 16) {
+    rc = pw_set_smem(pw_fwd_kernel<16>, smem);
+    if (!rc) pw_fwd_kernel<16><<<grid, PW_NT, smem, s>>>(op, G);
+  } else {
+    rc = pw_set_smem(pw_fwd_kernel<8>, smem);
+    if (!rc) pw_fwd_kernel<8><<<grid, PW_NT, smem, s>>>(op, G);
+  }
+  if (rc) return rc;
+  note_launch();
+  return check_launch("pw_fwd");
+}
+
+int launch_pw_bwd_data(const SeistOp& op, cudaStream_t s, int sm_count) {
+  const int cit = op.Cin > 8 ? 16 : 8;
+  const int Cout4 = (op.Cout + 3) & ~3;
+  const size_t smem = sizeof(PwChan) * cit + sizeof(PwOut) * Cout4 + sizeof(float) * ((size_t)Cout4 * cit + 4 * 2 * cit);
+  const long long nq = (long long)op.N * (op.L_out >> 2);
+  const int ty = (op.Cin + cit - 1) / cit;
+  const int G = pick_G(nq, ty, sm_count);
+  dim3 grid((unsigned)((nq + (long long)PW_NT * G - 1) / ((long long)PW_NT * G)), ty);
+  int rc = 0;
+  if (cit == 16) {
+    rc = pw_set_smem(pw_bwd_data_kernel<16>, smem);
+    if (!rc) pw_bwd_data_kernel<16><<<grid, PW_NT, smem, s>>>(op, G);
+  } else {
+    rc = pw_set_smem(pw_bwd_data_kernel<8>, smem);
+    if (!rc) pw_bwd_data_kernel<8><<<grid, PW_NT, smem, s>>>(op, G);
+  }
+  if (rc) return rc;
+  note_launch();
+  return check_launch("pw_bwd_data");
+}
+
+int launch_res_bwd4(const SeistOp& op, cudaStream_t s, int sm_count) {
+  const long long nq = (long long)op.N * (op.L_out >> 2);
+  const int G = pick_G(nq, op.Cout, sm_count);
+  dim3 grid((unsigned)((nq + (long long)PW_NT * G - 1) / ((long long)PW_NT * G)), op.Cout);
+  res_bwd4_kernel<<<grid, PW_NT, 0, s>>>(op, G);
+  note_launch();
+  return check_launch("res_bwd4");
+}
+
+}  // namespace seist
