@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIST_ABI_VERSION 4
+#define SEIST_ABI_VERSION 5
 #define SEIST_MAX_IN 3
 
 /* ---- BatchNorm table entry (nn.BatchNorm1d, models/seist.py:641) ---------------- */
@@ -94,7 +94,15 @@ enum SeistOpKind {
   /* per-channel coefficient tables of BN entries [bn_lo, bn_lo + n_bn): forward (scale, shift, mu,
      istd) once the statistics are complete; backward (A, Bx, Cc) once gstat is complete */
   SEIST_OP_BN_PREPARE_FWD = 13,
-  SEIST_OP_BN_PREPARE_BWD = 14
+  SEIST_OP_BN_PREPARE_BWD = 14,
+  /* DSConvNormAct (models/seist.py:124-155) is linear up to its BatchNorm: in_proj (1x1, no bias),
+     zero pad, depthwise k-tap, pconv (1x1, no bias) compose into ONE dense k-tap convolution
+       W_eff[o][i][t] = sum_c pconv[o][c] * dconv[c][t] * in_proj[c][i]
+     so the two intermediate tensors of every stem path never exist.  COMPOSE_FWD writes W_eff
+     (out.x) from in[0].x = in_proj [C,C], in[1].x = dconv [C,k], in[2].x = pconv [Cout,C];
+     COMPOSE_BWD scatters dW_eff (out.g) into in[0..2].g. */
+  SEIST_OP_STEM_COMPOSE_FWD = 15,
+  SEIST_OP_STEM_COMPOSE_BWD = 16
 };
 
 typedef struct SeistOp {

@@ -169,7 +169,14 @@ class Interp:
         return fac, alpha
 
     def _W(self, f: Op):
+        if f.Wx is not None:
+            return self.p.Wx[f.Wx.off:f.Wx.off + f.Wx.numel].view(f.Wx.shape).to(self.dt)
         return self.p.flat.P[f.W.off:f.W.off + f.W.numel].view(f.W.shape).to(self.dt)
+
+    def _parts(self, f: Op):
+        P = self.p.flat.P
+        i, d, pc = (P[r.off:r.off + r.numel].view(r.shape).double() for r in f.wparts)
+        return i[:, :, 0], d[:, 0, :], pc[:, :, 0]          # [C,C], [C,k], [Cout,C]
 
     def _bias(self, f: Op):
         return None if f.bias is None else self.p.flat.P[f.bias.off:f.bias.off + f.bias.numel].to(self.dt)
@@ -248,6 +255,10 @@ class Interp:
             f.out.buf.x[:, :, 0] = self._headvec_expr(f, self.value(f.ins[0])).float()
         elif f.kind == _lib.BN_FINALIZE_FWD:
             self.bn_finalize_fwd()
+        elif f.kind == _lib.STEM_COMPOSE_FWD:
+            i, d, pc = self._parts(f)
+            we = torch.einsum("oc,ct,ci->oit", pc, d, i)
+            self.p.Wx[f.Wx.off:f.Wx.off + f.Wx.numel] = we.reshape(-1).float()
         elif f.kind == _lib.BN_PREPARE_FWD:
             pass        # coefficients are evaluated on the fly here (bn_fwd / bn_khat)
         else:
@@ -312,6 +323,14 @@ class Interp:
         G = p.flat.G
         if op.kind == _lib.BN_PREPARE_BWD:
             return      # coefficients are evaluated on the fly here (bn_bwd)
+        if op.kind == _lib.STEM_COMPOSE_BWD:
+            i, d, pc = (t.detach().requires_grad_(True) for t in self._parts(f))
+            we = torch.einsum("oc,ct,ci->oit", pc, d, i)
+            dwe = p.dWx[f.Wx.off:f.Wx.off + f.Wx.numel].view(f.Wx.shape).double()
+            gi, gd, gp = torch.autograd.grad(we, [i, d, pc], dwe)
+            for r, gq in zip(f.wparts, (gi, gd, gp)):
+                G[r.off:r.off + r.numel] += gq.reshape(-1).float()
+            return
         if op.kind == _lib.ZERO:
             (op.out.buf.du if op.out.bn >= 0 else op.out.buf.dxd).zero_()
         elif op.kind == _lib.RES_BWD:
@@ -329,7 +348,10 @@ class Interp:
             Y = self._conv_expr(f, bases, W)
             if op.kind == _lib.CONV_BWD_W:
                 (dW,) = torch.autograd.grad(Y, W, gacc)
-                G[f.W.off:f.W.off + f.W.numel] += dW.reshape(-1).float()
+                if f.Wx is not None:
+                    p.dWx[f.Wx.off:f.Wx.off + f.Wx.numel] += dW.reshape(-1).float()
+                else:
+                    G[f.W.off:f.W.off + f.W.numel] += dW.reshape(-1).float()
                 if f.bias is not None:
                     G[f.bias.off:f.bias.off + f.bias.numel] += gacc.sum((0, 2)).float()
             else:
@@ -393,6 +415,7 @@ class Interp:
         p = self.p
         p.gstat.zero_()
         p.flat.G.zero_()
+        p.dWx.zero_()
         p.y_out.dxd.copy_(dy.view_as(p.y_out.dxd))
         for op in p.bwd_ops:
             self.run_bwd_op(op)

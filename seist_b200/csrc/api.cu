@@ -41,6 +41,7 @@ int launch_pw_bwd_data(const SeistOp& op, cudaStream_t s, int sm_count);
 int launch_res_bwd4(const SeistOp& op, cudaStream_t s, int sm_count);
 int launch_pw_bwd_w(const SeistOp& op, cudaStream_t s, int sm_count);
 int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s);
+int launch_stem_compose(const SeistOp& op, bool fwd, cudaStream_t s);
 
 static int sm_count() {
   if (g_sm_count == 0) {
@@ -77,6 +78,8 @@ static int run_one(const SeistOp& op, cudaStream_t s) {
     case SEIST_OP_BN_FINALIZE_BWD: return launch_bn_finalize(op, false, s);
     case SEIST_OP_BN_PREPARE_FWD: return launch_bn_prepare(op, true, s);
     case SEIST_OP_BN_PREPARE_BWD: return launch_bn_prepare(op, false, s);
+    case SEIST_OP_STEM_COMPOSE_FWD: return launch_stem_compose(op, true, s);
+    case SEIST_OP_STEM_COMPOSE_BWD: return launch_stem_compose(op, false, s);
     case SEIST_OP_ZERO: {
       cudaError_t e = cudaMemsetAsync(op.out.x, 0, op.zero_bytes, s);
       if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }

@@ -199,6 +199,53 @@ int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s) {
   return check_launch("bn_prepare");
 }
 
+// ---- stem path weight composition (SEIST_OP_STEM_COMPOSE_*) -----------------------------------------
+__global__ void stem_compose_fwd_kernel(const float* __restrict__ I, const float* __restrict__ D,
+                                        const float* __restrict__ P, float* __restrict__ We, int C, int Cout, int k) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < Cout * C * k; idx += gridDim.x * blockDim.x) {
+    const int t = idx % k, i = (idx / k) % C, o = idx / (k * C);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(P[o * C + c] * D[c * k + t], I[c * C + i], s);
+    We[idx] = s;
+  }
+}
+__global__ void stem_compose_bwd_kernel(const float* __restrict__ I, const float* __restrict__ D,
+                                        const float* __restrict__ P, const float* __restrict__ dWe, float* dI,
+                                        float* dD, float* dP, int C, int Cout, int k) {
+  const int nI = C * C, nD = C * k, nP = Cout * C;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nI + nD + nP; idx += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    if (idx < nI) {                       // dI[c][i] = sum_{o,t} dWe[o][i][t] P[o][c] D[c][t]
+      const int c = idx / C, i = idx % C;
+      for (int o = 0; o < Cout; ++o)
+        for (int t = 0; t < k; ++t) s = fmaf(dWe[(o * C + i) * k + t] * P[o * C + c], D[c * k + t], s);
+      dI[idx] += s;
+    } else if (idx < nI + nD) {           // dD[c][t] = sum_{o,i} dWe[o][i][t] P[o][c] I[c][i]
+      const int j = idx - nI, c = j / k, t = j % k;
+      for (int o = 0; o < Cout; ++o)
+        for (int i = 0; i < C; ++i) s = fmaf(dWe[(o * C + i) * k + t] * P[o * C + c], I[c * C + i], s);
+      dD[j] += s;
+    } else {                              // dP[o][c] = sum_{i,t} dWe[o][i][t] D[c][t] I[c][i]
+      const int j = idx - nI - nD, o = j / C, c = j % C;
+      for (int i = 0; i < C; ++i)
+        for (int t = 0; t < k; ++t) s = fmaf(dWe[(o * C + i) * k + t] * D[c * k + t], I[c * C + i], s);
+      dP[j] += s;
+    }
+  }
+}
+int launch_stem_compose(const SeistOp& op, bool fwd, cudaStream_t s) {
+  const int C = op.Cin, Cout = op.Cout, k = op.k;
+  if (fwd) {
+    stem_compose_fwd_kernel<<<(Cout * C * k + 255) / 256, 256, 0, s>>>(op.in[0].x, op.in[1].x, op.in[2].x, op.out.x, C,
+                                                                       Cout, k);
+  } else {
+    stem_compose_bwd_kernel<<<(C * C + C * k + Cout * C + 127) / 128, 128, 0, s>>>(
+        op.in[0].x, op.in[1].x, op.in[2].x, op.out.g, op.in[0].g, op.in[1].g, op.in[2].g, C, Cout, k);
+  }
+  note_launch();
+  return check_launch("stem_compose");
+}
+
 int launch_bn_finalize(const SeistOp& op, bool fwd, cudaStream_t s) {
   if (op.n_bn <= 0) return 0;
   if (fwd) bn_finalize_fwd_kernel<<<op.n_bn, 64, 0, s>>>(op.bn_table, op.n_bn);

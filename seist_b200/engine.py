@@ -112,6 +112,7 @@ class Engine:
         if fresh:
             flat.G.zero_()
         plan.gstat.zero_()
+        plan.dWx.zero_()
         plan.y_out.dxd.copy_(dy.reshape(plan.y_out.dxd.shape))
         self._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat)
         for name, p in self._named:

@@ -90,6 +90,8 @@ class Op:
     out: Optional[View] = None
     W: Optional[PRef] = None
     bias: Optional[PRef] = None
+    Wx: Optional[PRef] = None             # weights in the plan's scratch buffer (composed stem weights)
+    wparts: Optional[List[PRef]] = None   # STEM_COMPOSE: in_proj, dconv, pconv
     Cin: int = 0
     Cout: int = 0
     k: int = 1
@@ -221,6 +223,7 @@ class PlanBuilder:
         self.seed_ctr = 1
         self._bn_idx: Dict[str, int] = {}
         self._st_off = 0
+        self._wx_off = 0
 
     # ---- small helpers --------------------------------------------------------------------------
     def buf(self, name, C, L, no_grad=False) -> Buf:
@@ -257,7 +260,7 @@ class PlanBuilder:
 
     def conv(self, name, ins: List[View], wpath: str, out: View, *, k=1, stride=1, groups=1, pool=1,
              up_to: int = 0, pad: Optional[Tuple[int, int]] = None, res_a=None, res_b=None,
-             p_elem=0.0, p_path=0.0, p_alpha=0.0, out_act=OUT_NONE) -> Op:
+             p_elem=0.0, p_path=0.0, p_alpha=0.0, out_act=OUT_NONE, wx: Optional[PRef] = None) -> Op:
         src_L = ins[0].L
         for v in ins:
             assert v.L == src_L
@@ -272,10 +275,10 @@ class PlanBuilder:
         L_out = (L_in + pad[0] + pad[1] - k) // stride + 1
         assert L_out == out.L, (name, L_out, out.L)
         Cin = sum(v.C for v in ins)
-        W = self.pref(wpath + ".weight")
-        assert W.shape == (out.C, Cin // groups, k), (name, W.shape, out.C, Cin, groups, k)
-        op = Op(_lib.CONV_FWD, self.N, ins=ins, res_a=res_a, res_b=res_b, out=out, W=W,
-                bias=self.pref(wpath + ".bias"), Cin=Cin, Cout=out.C, k=k, stride=stride, pad_left=pad[0],
+        W = self.pref(wpath + ".weight") if wx is None else None
+        assert (wx or W).shape == (out.C, Cin // groups, k), (name, (wx or W).shape, out.C, Cin, groups, k)
+        op = Op(_lib.CONV_FWD, self.N, ins=ins, res_a=res_a, res_b=res_b, out=out, W=W, Wx=wx,
+                bias=self.pref(wpath + ".bias") if wx is None else None, Cin=Cin, Cout=out.C, k=k, stride=stride, pad_left=pad[0],
                 groups=groups, pool=pool, up_src_L=(src_L if up_to > 0 else 0), L_in=L_in, L_out=L_out,
                 out_act=out_act, p_elem=self.drop(p_elem), p_path=self.drop(p_path),
                 p_alpha=self.drop(p_alpha), name=name)
@@ -311,12 +314,16 @@ class PlanBuilder:
         for j in range(3):
             k = k0 + 4 * j
             pj = f"{p}.convs.{j}"
-            t1 = self.buf(f"{pj}.t1", cin, L_in)
-            self.conv(f"{pj}.in_proj", [vin], f"{pj}.in_proj", View(t1, 0, cin))
-            t2 = self.buf(f"{pj}.t2", cin, L_out)
-            self.conv(f"{pj}.dconv", [View(t1, 0, cin)], f"{pj}.dconv", View(t2, 0, cin), k=k, stride=s, groups=cin)
+            # in_proj -> pad -> depthwise -> pconv is linear: run it as ONE dense k-tap conv whose weights
+            # are composed on the device each step (SEIST_OP_STEM_COMPOSE_*); no intermediate tensors.
+            parts = [self.pref(f"{pj}.in_proj.weight"), self.pref(f"{pj}.dconv.weight"), self.pref(f"{pj}.pconv.weight")]
+            wx = PRef(self._wx_off, cout * cin * k, (cout, cin, k))
+            self._wx_off += (wx.numel + 3) // 4 * 4
+            self.plan.fwd_ops.append(Op(_lib.STEM_COMPOSE_FWD, self.N, Wx=wx, wparts=parts, Cin=cin, Cout=cout, k=k,
+                                        name=f"{pj}.compose"))
             b = self.bn(f"{pj}.norm", L_out)
-            self.conv(f"{pj}.pconv", [View(t2, 0, cin)], f"{pj}.pconv", View(cat, j * cout, cout, bn=b))
+            self.conv(f"{pj}.conv", [View(vin.buf, vin.c0, vin.C, vin.bn, vin.bn_c0, vin.act)], pj, View(cat, j * cout, cout, bn=b),
+                      k=k, stride=s, wx=wx)
             views.append(View(cat, j * cout, cout, bn=b, act=ACT_GELU))
         w = self.buf(f"{p}.out", cout, L_out)
         b = self.bn(f"{p}.norm", L_out)
@@ -482,6 +489,7 @@ class PlanBuilder:
                 blk += 1
         pl.y_out = self.head_dpk(cur, self.Lx) if hp.head == "dpk" else self.head_vec(cur)
         pl.y_out.need_dxd = True
+        pl.wx_numel = self._wx_off
         if self.training:
             pl.fwd_ops.append(Op(_lib.BN_FINALIZE_FWD, self.N, name="bn_finalize_fwd"))
         pl.fwd_ops = self._insert_prepares(pl.fwd_ops, forward=True)
@@ -533,6 +541,8 @@ class PlanBuilder:
             elif f.kind == _lib.HEADVEC_FWD:
                 t = grad_target(f.ins[0])
                 ops.append(Op(_lib.HEADVEC_BWD, f.N, ins=[t], out=f.out, fwd=f, name=f.name + ":bwd"))
+            elif f.kind == _lib.STEM_COMPOSE_FWD:
+                ops.append(Op(_lib.STEM_COMPOSE_BWD, f.N, fwd=f, name=f.name + ":bwd"))
             elif f.kind == _lib.BN_FINALIZE_FWD:
                 pass
         ops.append(Op(_lib.BN_FINALIZE_BWD, self.N, name="bn_finalize_bwd"))
@@ -611,6 +621,8 @@ def allocate(plan: Plan, with_backward: bool):
     nst = max(sum(2 * e.C for e in plan.bns), 2)
     plan.stat = torch.zeros(nst, dtype=torch.float64, device=dev)
     plan.gstat = torch.zeros(nst, dtype=torch.float64, device=dev)
+    plan.Wx = torch.zeros(max(getattr(plan, "wx_numel", 0), 4), dtype=torch.float32, device=dev)
+    plan.dWx = torch.zeros_like(plan.Wx)
     plan.coef = torch.zeros(4 * nst, dtype=torch.float32, device=dev)   # [C][8] per BN entry
     plan.step_seed = torch.zeros(1, dtype=torch.int64, device=dev)
 
@@ -695,6 +707,15 @@ def to_c(plan: Plan, ops: List[Op]):
         if f.W is not None:
             c.W = flat.P.data_ptr() + 4 * f.W.off
             c.dW = flat.G.data_ptr() + 4 * f.W.off
+        if f.Wx is not None:
+            c.W = plan.Wx.data_ptr() + 4 * f.Wx.off
+            c.dW = plan.dWx.data_ptr() + 4 * f.Wx.off
+        if f.kind == _lib.STEM_COMPOSE_FWD:
+            for j, r in enumerate(f.wparts):
+                c.inp[j].x = flat.P.data_ptr() + 4 * r.off
+                c.inp[j].g = flat.G.data_ptr() + 4 * r.off
+            c.out.x = plan.Wx.data_ptr() + 4 * f.Wx.off
+            c.out.g = plan.dWx.data_ptr() + 4 * f.Wx.off
         if f.bias is not None:
             c.bias = flat.P.data_ptr() + 4 * f.bias.off
             c.dbias = flat.G.data_ptr() + 4 * f.bias.off

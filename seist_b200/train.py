@@ -113,6 +113,7 @@ class Trainer:
                                            self.loss_fn.delta, dy.data_ptr(), s))
         flat.G.zero_()
         plan.gstat.zero_()
+        plan.dWx.zero_()
         eng._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat)
         gscale = 1.0
         if self.world > 1:

@@ -61,6 +61,8 @@ def push_state(p_cpu, p_gpu):
     p_gpu.flat.G.copy_(p_cpu.flat.G)
     p_gpu.flat.RB.copy_(p_cpu.flat.RB)
     p_gpu.step_seed.copy_(p_cpu.step_seed)
+    p_gpu.Wx.copy_(p_cpu.Wx)
+    p_gpu.dWx.copy_(p_cpu.dWx)
 
 
 def run_gpu_op(p_gpu, c_ops, i):

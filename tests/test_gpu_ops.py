@@ -54,6 +54,8 @@ def test_ops_match_interpreter(name, N, L, training, drops):
             errs.append(("lse",) + rel_err(fg.lse, fc.lse))
         if fc.kind == _lib.BN_FINALIZE_FWD:
             errs.append(("running",) + rel_err(p_gpu.flat.RB, p_cpu.flat.RB))
+        if fc.kind == _lib.STEM_COMPOSE_FWD:
+            errs.append(("W_eff",) + rel_err(p_gpu.Wx, p_cpu.Wx))
         for what, err, ref in errs:
             if not err < TOL:
                 failures.append(f"fwd[{i}] {fc.name} {what}: rel {err:.3e} (max {ref:.3e})")
@@ -64,6 +66,7 @@ def test_ops_match_interpreter(name, N, L, training, drops):
     # backward, seeded with a smooth gradient
     p_cpu.gstat.zero_()
     p_cpu.flat.G.zero_()
+    p_cpu.dWx.zero_()
     g = torch.Generator().manual_seed(2)
     p_cpu.y_out.dxd.copy_(torch.randn(p_cpu.y_out.dxd.shape, generator=g) / p_cpu.y_out.dxd[0].numel() ** 0.5)
     for i, (bc, bg) in enumerate(zip(p_cpu.bwd_ops, p_gpu.bwd_ops)):
@@ -86,8 +89,9 @@ def test_ops_match_interpreter(name, N, L, training, drops):
                 b = (tc.buf.du if tc.bn >= 0 else tc.buf.dxd)[:, sl]
                 errs.append((f"grad({tc.buf.name})",) + rel_err(a, b))
             errs.append(("gstat",) + rel_err(p_gpu.gstat, p_cpu.gstat))
-        if bc.kind in (_lib.CONV_BWD_W, _lib.HEADVEC_BWD, _lib.BN_FINALIZE_BWD):
+        if bc.kind in (_lib.CONV_BWD_W, _lib.HEADVEC_BWD, _lib.BN_FINALIZE_BWD, _lib.STEM_COMPOSE_BWD):
             errs.append(("G",) + rel_err(p_gpu.flat.G, p_cpu.flat.G))
+            errs.append(("dWx",) + rel_err(p_gpu.dWx, p_cpu.dWx))
         for what, err, ref in errs:
             if not err < TOL:
                 failures.append(f"bwd[{i}] {bc.name} {what}: rel {err:.3e} (max {ref:.3e})")
