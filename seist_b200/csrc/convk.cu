@@ -1,0 +1,612 @@
+// Dense (groups == 1) k-tap convolutions: the composed stem paths (k = 5..19, stride 1/2, reference
+// models/seist.py:124-155) and the up-sampling head (k = 7/11 behind F.interpolate(linear), :536,:566).
+//
+// Tile: 256 threads = WC channel-warps x WP sample-warps; a thread owns 4 CONSECUTIVE output samples x 8
+// output channels.  The (channel, sample) input tile with halo is staged once per 8-channel chunk with
+// BN-apply / GELU / linear up-sampling / zero padding evaluated on the way in; per reduction channel a
+// thread pulls its sliding window (3*S + K samples) with 16-byte shared loads and reuses every window
+// element for up to K taps x 8 channels (K and S are template parameters so the window lives in
+// registers).  The same engine run with flipped/transposed weights over the BN-backward-combined output
+// gradient is the data gradient (stride 1).  The weight gradient keeps lanes on the sample axis: a warp
+// owns a (4 co) x (TCI ci) x K tile of dW in registers and reduces it over lanes once per CTA lifetime.
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace seist {
+
+constexpr int CK_NT = 256;
+constexpr int CK_CIC = 8;
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int K, int S>
+struct CkWin {
+  static constexpr int WIN = 3 * S + K;
+  static constexpr int NV = (WIN + 3) / 4;
+};
+
+// acc[c][j] += sum_t w[t][c] * win[j*S + t] for one reduction channel
+template <int K, int S>
+__device__ __forceinline__ void ck_accumulate(const float* irow, const float* wrow, int wstride, float (&acc)[8][4]) {
+  constexpr int NV = CkWin<K, S>::NV;
+  float win[NV * 4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 q = lds4(irow + 4 * v);
+    win[4 * v] = q.x;
+    win[4 * v + 1] = q.y;
+    win[4 * v + 2] = q.z;
+    win[4 * v + 3] = q.w;
+  }
+#pragma unroll
+  for (int t = 0; t < K; ++t) {
+    const float4 w0 = lds4(wrow + t * wstride), w1 = lds4(wrow + t * wstride + 4);
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v = win[j * S + t];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c][j] = fmaf(w[c], v, acc[c][j]);
+    }
+  }
+}
+
+// stage rows of the consumer view (conv-input coordinates p_base .. p_base + width) — 8 loads in flight
+__device__ __forceinline__ void ck_stage_input(const SeistOp& op, int n, int ci0, int cic, float* in_s, int pitch,
+                                               int width, int p_base, int Lsrc, float ratio) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool plain = op.up_src_L == 0;
+  for (int r = warp; r < CK_CIC; r += CK_NT / 32) {
+    float* dst = in_s + r * pitch;
+    if (r >= cic) {
+      for (int pos = lane; pos < width; pos += 32) dst[pos] = 0.f;
+      continue;
+    }
+    const RowSrc rs = make_row(op, n, ci0 + r);
+    if (plain) {
+      for (int pos0 = lane; pos0 < width; pos0 += 32 * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int p = p_base + pos0 + 32 * u;
+          v[u] = (pos0 + 32 * u < width && p >= 0 && p < op.L_in) ? rs.x[p] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int pos = pos0 + 32 * u, p = p_base + pos;
+          if (pos < width) {
+            float t = fmaf(rs.sc, v[u], rs.sh);
+            if (rs.act == SEIST_ACT_GELU) t = gelu_f(t);
+            dst[pos] = (p >= 0 && p < op.L_in) ? t : 0.f;
+          }
+        }
+      }
+    } else {
+      for (int pos = lane; pos < width; pos += 32) dst[pos] = conv_input_at(op, rs, p_base + pos, Lsrc, ratio);
+    }
+  }
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+template <int K, int S>
+__global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant__ SeistOp op, const int WC) {
+  extern __shared__ __align__(16) float ck_smem[];
+  const int WP = 8 / WC, CO_B = 8 * WC, TLo = 128 * WP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wc = warp % WC, wp = warp / WC;
+  const int n = blockIdx.y, l0 = blockIdx.x * TLo, co_base = blockIdx.z * CO_B;
+  const int width = TLo * S + K - S;
+  const int pitch = ((width + 3) & ~3) + 4;
+  float* in_s = ck_smem;                               // [CIC][pitch]
+  float* w_s = ck_smem + CK_CIC * pitch;               // [CIC][K][CO_B]
+  float* red_s = w_s + CK_CIC * K * CO_B;              // [8 warps][16]
+  const int Lsrc = op.in[0].L;
+  const float ratio = op.up_src_L > 0 ? (float)Lsrc / (float)op.L_in : 1.f;
+  const int p_base = l0 * S - op.pad_left;
+
+  float acc[8][4];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+
+  for (int ci0 = 0; ci0 < op.Cin; ci0 += CK_CIC) {
+    const int cic = min(CK_CIC, op.Cin - ci0);
+    ck_stage_input(op, n, ci0, cic, in_s, pitch, width, p_base, Lsrc, ratio);
+    for (int idx = tid; idx < CK_CIC * K * CO_B; idx += CK_NT) {
+      const int col = idx % CO_B, rest = idx / CO_B;
+      const int t = rest % K, r = rest / K;
+      const int co = co_base + col;
+      w_s[idx] = (r < cic && co < op.Cout) ? op.W[((size_t)co * op.Cin + ci0 + r) * K + t] : 0.f;
+    }
+    __syncthreads();
+    const float* ib = in_s + (wp * 128 + 4 * lane) * S;
+    const float* wb = w_s + wc * 8;
+    for (int r = 0; r < cic; ++r) ck_accumulate<K, S>(ib + r * pitch, wb + r * K * CO_B, CO_B, acc);
+    __syncthreads();
+  }
+
+  // ---- epilogue ----------------------------------------------------------------------------------
+  const uint64_t seed = load_seed(op.step_seed);
+  const float pf = path_factor(op, seed, n), af = alpha_factor(op, seed, n);
+  const bool stats = (op.out.bn >= 0) && op.bn_table[op.out.bn >= 0 ? op.out.bn : 0].use_batch;
+  const int lq = l0 + wp * 128 + 4 * lane;
+  const bool vec = (op.L_out & 3) == 0;
+  float st[16];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int co = co_base + wc * 8 + c;
+    float s1 = 0.f, s2 = 0.f;
+    if (co < op.Cout) {
+      const float b = op.bias ? op.bias[co] : 0.f;
+      float asc = 1.f, ash = 0.f, bsc = 1.f, bsh = 0.f;
+      const float *ra = nullptr, *rb = nullptr;
+      if (op.res_a.C > 0) {
+        view_coef(op, op.res_a, co, asc, ash);
+        ra = view_row(op.res_a, n, co);
+      }
+      if (op.res_b.C > 0) {
+        view_coef(op, op.res_b, co, bsc, bsh);
+        rb = view_row(op.res_b, n, co);
+      }
+      float* orow = op.out.x + ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)op.L_out;
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int l = lq + j;
+        float v = 0.f;
+        if (l < op.L_out) {
+          v = (acc[c][j] + b) * pf * elem_factor(op, seed, n, co, l);
+          if (ra) v += fmaf(asc, ra[l], ash);
+          v *= af;
+          if (rb) v += fmaf(bsc, rb[l], bsh);
+          if (op.out_act == SEIST_OUT_SIGMOID) v = sigmoid_f(v);
+          s1 += v;
+          s2 = fmaf(v, v, s2);
+        }
+        r[j] = v;
+      }
+      if (vec && lq + 3 < op.L_out) {
+        *reinterpret_cast<float4*>(orow + lq) = make_float4(r[0], r[1], r[2], r[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (lq + j < op.L_out) orow[lq + j] = r[j];
+      }
+    }
+    st[2 * c] = s1;
+    st[2 * c + 1] = s2;
+  }
+  if (stats) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float s = warp_sum(st[i]);
+      if (lane == 0) red_s[warp * 16 + i] = s;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < WC * 16; idx += CK_NT) {
+      const int w0 = idx / 16, i = idx % 16;
+      float s = 0.f;
+      for (int p = 0; p < WP; ++p) s += red_s[(p * WC + w0) * 16 + i];
+      const int co = co_base + w0 * 8 + (i >> 1);
+      if (co < op.Cout) {
+        const SeistBN& e = op.bn_table[op.out.bn];
+        atomicAdd(&e.stat[(i & 1) * e.C + op.out.bn_c0 + co], (double)s);
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// backward (data), stride 1:  d in[ci][p] = sum_{co,t} W[co][ci][t] gacc[co][p + pad_left - t]
+// ================================================================================================
+template <int K>
+__global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_constant__ SeistOp op, const int WC) {
+  extern __shared__ __align__(16) float ck_smem[];
+  const int WP = 8 / WC, CI_B = 8 * WC, TLo = 128 * WP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wc = warp % WC, wp = warp / WC;
+  const int n = blockIdx.y, p0 = blockIdx.x * TLo, ci_base = blockIdx.z * CI_B;
+  const int width = TLo + K - 1;
+  const int pitch = ((width + 3) & ~3) + 4;
+  float* z_s = ck_smem;                                // [CIC][pitch]
+  float* w_s = ck_smem + CK_CIC * pitch;               // [CIC][K][CI_B]
+  float* red_s = w_s + CK_CIC * K * CI_B;              // [8][16]
+  const uint64_t seed = load_seed(op.step_seed);
+  const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
+  const int m_base = p0 + op.pad_left - (K - 1);       // output-sample coordinate of z_s[.][0]
+
+  float acc[8][4];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+
+  for (int co0 = 0; co0 < op.Cout; co0 += CK_CIC) {
+    const int coc = min(CK_CIC, op.Cout - co0);
+    for (int r = warp; r < CK_CIC; r += CK_NT / 32) {
+      float* dst = z_s + r * pitch;
+      if (r >= coc) {
+        for (int pos = lane; pos < width; pos += 32) dst[pos] = 0.f;
+        continue;
+      }
+      const int co = co0 + r;
+      const OutGradCoef kc = out_grad_coef(op, co);
+      for (int pos0 = lane; pos0 < width; pos0 += 32 * 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pos = pos0 + 32 * u, m = m_base + pos;
+          v[u] = (pos < width && m >= 0 && m < op.L_out) ? out_grad_at(op, kc, n, co, m) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pos = pos0 + 32 * u, m = m_base + pos;
+          if (pos < width) {
+            float t = v[u] * pf;
+            if (op.p_elem > 0.f && m >= 0 && m < op.L_out) t *= elem_factor(op, seed, n, co, m);
+            dst[pos] = t;
+          }
+        }
+      }
+    }
+    // flipped + transposed weights: w_s[(r*K + tf)*CI_B + col] = W[co0+r][ci_base+col][K-1-tf]
+    for (int idx = tid; idx < CK_CIC * K * CI_B; idx += CK_NT) {
+      const int col = idx % CI_B, rest = idx / CI_B;
+      const int tf = rest % K, r = rest / K;
+      const int ci = ci_base + col;
+      w_s[idx] = (r < coc && ci < op.Cin) ? op.W[((size_t)(co0 + r) * op.Cin + ci) * K + (K - 1 - tf)] : 0.f;
+    }
+    __syncthreads();
+    const float* zb = z_s + wp * 128 + 4 * lane;
+    const float* wb = w_s + wc * 8;
+    for (int r = 0; r < coc; ++r) ck_accumulate<K, 1>(zb + r * pitch, wb + r * K * CI_B, CI_B, acc);
+    __syncthreads();
+  }
+
+  // ---- route to the source view ----------------------------------------------------------------------
+  const int Lsrc = op.in[0].L;
+  const float ratio = op.up_src_L > 0 ? (float)Lsrc / (float)op.L_in : 1.f;
+  const int pq = p0 + wp * 128 + 4 * lane;
+  float st[16];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int ci = ci_base + wc * 8 + c;
+    float s1 = 0.f, s2 = 0.f;
+    if (ci < op.Cin) {
+      int cv;
+      const int vi = resolve_view(op, ci, cv);
+      const SeistView& v = op.in[vi];
+      if (v.g != nullptr) {
+        float sc, sh, mu = 0.f, istd = 0.f;
+        view_coef(op, v, cv, sc, sh);
+        if (v.bn >= 0) view_khat(op, v, cv, mu, istd);
+        const float* xr = view_row(v, n, cv);
+        float* gr = view_grad_row(v, n, cv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int p = pq + j;
+          if (p >= op.L_in) continue;
+          const float d = acc[c][j];
+          if (op.up_src_L > 0) {
+            int i0, i1;
+            float lam;
+            upsample_coords(p, ratio, Lsrc, i0, i1, lam);
+            const float x0 = xr[i0], x1 = xr[i1];
+            float g0 = d * (1.f - lam), g1 = d * lam;
+            if (v.act == SEIST_ACT_GELU) {
+              g0 *= gelu_grad_f(fmaf(sc, x0, sh));
+              g1 *= gelu_grad_f(fmaf(sc, x1, sh));
+            }
+            atomicAdd(&gr[i0], g0);
+            atomicAdd(&gr[i1], g1);
+            s1 += g0 + g1;
+            s2 = fmaf(g0, (x0 - mu) * istd, s2);
+            s2 = fmaf(g1, (x1 - mu) * istd, s2);
+          } else {
+            const float x = xr[p];
+            float g = d;
+            if (v.act == SEIST_ACT_GELU) g *= gelu_grad_f(fmaf(sc, x, sh));
+            if (v.accum) gr[p] += g; else gr[p] = g;
+            s1 += g;
+            s2 = fmaf(g, (x - mu) * istd, s2);
+          }
+        }
+      }
+    }
+    st[2 * c] = s1;
+    st[2 * c + 1] = s2;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float s = warp_sum(st[i]);
+    if (lane == 0) red_s[warp * 16 + i] = s;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < WC * 16; idx += CK_NT) {
+    const int w0 = idx / 16, i = idx % 16;
+    float s = 0.f;
+    for (int p = 0; p < WP; ++p) s += red_s[(p * WC + w0) * 16 + i];
+    const int ci = ci_base + w0 * 8 + (i >> 1);
+    if (ci < op.Cin) {
+      int cv;
+      const int vi = resolve_view(op, ci, cv);
+      const SeistView& v = op.in[vi];
+      if (v.g != nullptr && v.bn >= 0) {
+        const SeistBN& e = op.bn_table[v.bn];
+        atomicAdd(&e.gstat[(i & 1) * e.C + v.bn_c0 + cv], (double)s);
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// backward (weights): dW[co][ci][t] = sum_{n,l} gacc[co][l] * convin[ci][l*S + t - pad_left]
+// warp (wm, wn) owns co in [4*wm, 4*wm+4) x ci in [TCI*wn, TCI*(wn+1)) x all K taps; lanes = sample quads
+// ================================================================================================
+template <int K, int S, int TCI>
+__global__ void __launch_bounds__(CK_NT) convk_bwd_w_kernel(const __grid_constant__ SeistOp op, const int WM) {
+  extern __shared__ __align__(16) float ck_smem[];
+  constexpr int PCW = 128;                               // output samples per chunk (one quad per lane)
+  constexpr int NV = CkWin<K, S>::NV;
+  const int WN = 8 / WM, CO_B = 4 * WM, CI_B = TCI * WN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WM, wn = warp / WM;
+  const int co_base = blockIdx.y * CO_B, ci_base = blockIdx.z * CI_B;
+  const int width = PCW * S + K - S;
+  const int pitch = ((width + 3) & ~3) + 4;
+  constexpr int GPITCH = PCW + 4;
+  float* g_s = ck_smem;                                  // [CO_B][GPITCH]
+  float* in_s = ck_smem + CO_B * GPITCH;                 // [CI_B][pitch]
+  const uint64_t seed = load_seed(op.step_seed);
+  const int Lsrc = op.in[0].L;
+  const float ratio = op.up_src_L > 0 ? (float)Lsrc / (float)op.L_in : 1.f;
+  const bool plain = op.up_src_L == 0;
+
+  float acc[4][TCI][K];
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < TCI; ++c)
+#pragma unroll
+      for (int t = 0; t < K; ++t) acc[i][c][t] = 0.f;
+
+  const int chunks_per_n = (op.L_out + PCW - 1) / PCW;
+  const int total = op.N * chunks_per_n;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = tile / chunks_per_n;
+    const int l0 = (tile - n * chunks_per_n) * PCW;
+    const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
+    // gacc rows
+    for (int r = warp; r < CO_B; r += CK_NT / 32) {
+      const int co = co_base + r;
+      float v[4];
+      OutGradCoef kc = {0.f, 0.f, 0.f};
+      if (co < op.Cout) kc = out_grad_coef(op, co);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int l = l0 + lane + 32 * u;
+        v[u] = (co < op.Cout && l < op.L_out) ? out_grad_at(op, kc, n, co, l) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int l = l0 + lane + 32 * u;
+        float t = v[u] * pf;
+        if (op.p_elem > 0.f && co < op.Cout && l < op.L_out) t *= elem_factor(op, seed, n, co, l);
+        g_s[r * GPITCH + lane + 32 * u] = t;
+      }
+    }
+    // conv-input rows
+    const int p_base = l0 * S - op.pad_left;
+    for (int r = warp; r < CI_B; r += CK_NT / 32) {
+      const int ci = ci_base + r;
+      float* dst = in_s + r * pitch;
+      if (ci >= op.Cin) {
+        for (int pos = lane; pos < width; pos += 32) dst[pos] = 0.f;
+        continue;
+      }
+      const RowSrc rs = make_row(op, n, ci);
+      if (plain) {
+        for (int pos0 = lane; pos0 < width; pos0 += 32 * 4) {
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int p = p_base + pos0 + 32 * u;
+            v[u] = (pos0 + 32 * u < width && p >= 0 && p < op.L_in) ? rs.x[p] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int pos = pos0 + 32 * u, p = p_base + pos;
+            if (pos < width) {
+              float t = fmaf(rs.sc, v[u], rs.sh);
+              if (rs.act == SEIST_ACT_GELU) t = gelu_f(t);
+              dst[pos] = (p >= 0 && p < op.L_in) ? t : 0.f;
+            }
+          }
+        }
+      } else {
+        for (int pos = lane; pos < width; pos += 32) dst[pos] = conv_input_at(op, rs, p_base + pos, Lsrc, ratio);
+      }
+    }
+    __syncthreads();
+    {
+      float4 gq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gq[i] = lds4(g_s + (wm * 4 + i) * GPITCH + 4 * lane);
+#pragma unroll
+      for (int c = 0; c < TCI; ++c) {
+        const float* irow = in_s + (wn * TCI + c) * pitch + 4 * lane * S;
+        float win[NV * 4];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float4 q = lds4(irow + 4 * v);
+          win[4 * v] = q.x;
+          win[4 * v + 1] = q.y;
+          win[4 * v + 2] = q.z;
+          win[4 * v + 3] = q.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int t = 0; t < K; ++t) {
+            float a = acc[i][c][t];
+            a = fmaf(gq[i].x, win[t], a);
+            a = fmaf(gq[i].y, win[S + t], a);
+            a = fmaf(gq[i].z, win[2 * S + t], a);
+            a = fmaf(gq[i].w, win[3 * S + t], a);
+            acc[i][c][t] = a;
+          }
+      }
+      if (wn == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bacc[i] += (gq[i].x + gq[i].y) + (gq[i].z + gq[i].w);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co_base + wm * 4 + i;
+#pragma unroll
+    for (int c = 0; c < TCI; ++c) {
+      const int ci = ci_base + wn * TCI + c;
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        const float s = warp_sum(acc[i][c][t]);
+        if (lane == 0 && co < op.Cout && ci < op.Cin) atomicAdd(&op.dW[((size_t)co * op.Cin + ci) * K + t], s);
+      }
+    }
+    if (wn == 0 && blockIdx.z == 0 && op.dbias != nullptr) {
+      const float s = warp_sum(bacc[i]);
+      if (lane == 0 && co < op.Cout) atomicAdd(&op.dbias[co], s);
+    }
+  }
+}
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+bool convk_eligible(const SeistOp& op) {
+  if (op.groups != 1 || op.pool > 1 || op.n_in != 1) return false;
+  if (op.stride != 1 && op.stride != 2) return false;
+  switch (op.k) {
+    case 3: case 5: case 7: case 9: case 11: case 13: case 15: case 19: break;
+    default: return false;
+  }
+  if (op.stride == 2 && !(op.k == 7 || op.k == 11 || op.k == 15 || op.k == 19)) return false;
+  return true;
+}
+
+template <typename Kf>
+static int ck_set_smem(Kf kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+static int pick_wc(int channels) { return channels > 32 ? 8 : (channels > 16 ? 4 : (channels > 8 ? 2 : 1)); }
+
+template <int K, int S>
+static int launch_fwd_ks(const SeistOp& op, cudaStream_t s) {
+  const int WC = pick_wc(op.Cout), WP = 8 / WC, CO_B = 8 * WC, TLo = 128 * WP;
+  const int width = TLo * S + K - S, pitch = ((width + 3) & ~3) + 4;
+  const size_t smem = sizeof(float) * ((size_t)CK_CIC * pitch + (size_t)CK_CIC * K * CO_B + 8 * 16);
+  dim3 grid((op.L_out + TLo - 1) / TLo, op.N, (op.Cout + CO_B - 1) / CO_B);
+  int rc = ck_set_smem(convk_fwd_kernel<K, S>, smem);
+  if (rc) return rc;
+  convk_fwd_kernel<K, S><<<grid, CK_NT, smem, s>>>(op, WC);
+  note_launch();
+  return check_launch("convk_fwd");
+}
+
+template <int K>
+static int launch_bwdd_k(const SeistOp& op, cudaStream_t s) {
+  const int WC = pick_wc(op.Cin), WP = 8 / WC, CI_B = 8 * WC, TLo = 128 * WP;
+  const int width = TLo + K - 1, pitch = ((width + 3) & ~3) + 4;
+  const size_t smem = sizeof(float) * ((size_t)CK_CIC * pitch + (size_t)CK_CIC * K * CI_B + 8 * 16);
+  dim3 grid((op.L_in + TLo - 1) / TLo, op.N, (op.Cin + CI_B - 1) / CI_B);
+  int rc = ck_set_smem(convk_bwd_data_kernel<K>, smem);
+  if (rc) return rc;
+  convk_bwd_data_kernel<K><<<grid, CK_NT, smem, s>>>(op, WC);
+  note_launch();
+  return check_launch("convk_bwd_data");
+}
+
+template <int K, int S, int TCI>
+static int launch_bwdw_ks(const SeistOp& op, cudaStream_t s, int sm_count) {
+  // warp grid: WM co-tiles (4 channels) x WN ci-tiles (TCI channels)
+  int WM = op.Cout > 16 ? 8 : (op.Cout > 8 ? 4 : (op.Cout > 4 ? 2 : 1));
+  const int WN = 8 / WM, CO_B = 4 * WM, CI_B = TCI * WN;
+  const int width = 128 * S + K - S, pitch = ((width + 3) & ~3) + 4;
+  const size_t smem = sizeof(float) * ((size_t)CO_B * 132 + (size_t)CI_B * pitch);
+  const int gy = (op.Cout + CO_B - 1) / CO_B, gz = (op.Cin + CI_B - 1) / CI_B;
+  const long tiles = (long)op.N * ((op.L_out + 127) / 128);
+  long gx = (3L * sm_count + gy * gz - 1) / (gy * gz);
+  if (gx > tiles) gx = tiles;
+  if (gx < 1) gx = 1;
+  int rc = ck_set_smem(convk_bwd_w_kernel<K, S, TCI>, smem);
+  if (rc) return rc;
+  convk_bwd_w_kernel<K, S, TCI><<<dim3((unsigned)gx, gy, gz), CK_NT, smem, s>>>(op, WM);
+  note_launch();
+  return check_launch("convk_bwd_w");
+}
+
+#define CK_SWITCH_K(FN, ...)              \
+  switch (op.k) {                         \
+    case 3: return FN(3, __VA_ARGS__);    \
+    case 5: return FN(5, __VA_ARGS__);    \
+    case 7: return FN(7, __VA_ARGS__);    \
+    case 9: return FN(9, __VA_ARGS__);    \
+    case 11: return FN(11, __VA_ARGS__);  \
+    case 13: return FN(13, __VA_ARGS__);  \
+    case 15: return FN(15, __VA_ARGS__);  \
+    default: return FN(19, __VA_ARGS__);  \
+  }
+
+int launch_convk_fwd(const SeistOp& op, cudaStream_t s) {
+  if (op.stride == 2) {
+    switch (op.k) {
+      case 7: return launch_fwd_ks<7, 2>(op, s);
+      case 11: return launch_fwd_ks<11, 2>(op, s);
+      case 15: return launch_fwd_ks<15, 2>(op, s);
+      default: return launch_fwd_ks<19, 2>(op, s);
+    }
+  }
+#define FWD1(KK, dummy) launch_fwd_ks<KK, 1>(op, s)
+  CK_SWITCH_K(FWD1, 0)
+#undef FWD1
+}
+
+int launch_convk_bwd_data(const SeistOp& op, cudaStream_t s) {
+#define BD(KK, dummy) launch_bwdd_k<KK>(op, s)
+  CK_SWITCH_K(BD, 0)
+#undef BD
+}
+
+int launch_convk_bwd_w(const SeistOp& op, cudaStream_t s, int sm_count) {
+  if (op.stride == 2) {
+    switch (op.k) {
+      case 7: return launch_bwdw_ks<7, 2, 4>(op, s, sm_count);
+      case 11: return launch_bwdw_ks<11, 2, 2>(op, s, sm_count);
+      case 15: return launch_bwdw_ks<15, 2, 1>(op, s, sm_count);
+      default: return launch_bwdw_ks<19, 2, 1>(op, s, sm_count);
+    }
+  }
+  switch (op.k) {
+    case 3: return launch_bwdw_ks<3, 1, 4>(op, s, sm_count);
+    case 5: return launch_bwdw_ks<5, 1, 4>(op, s, sm_count);
+    case 7: return launch_bwdw_ks<7, 1, 4>(op, s, sm_count);
+    case 9: return launch_bwdw_ks<9, 1, 2>(op, s, sm_count);
+    case 11: return launch_bwdw_ks<11, 1, 2>(op, s, sm_count);
+    case 13: return launch_bwdw_ks<13, 1, 1>(op, s, sm_count);
+    case 15: return launch_bwdw_ks<15, 1, 1>(op, s, sm_count);
+    default: return launch_bwdw_ks<19, 1, 1>(op, s, sm_count);
+  }
+}
+
+}  // namespace seist
