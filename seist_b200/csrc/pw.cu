@@ -8,6 +8,7 @@
 // reduction channel).  A CTA runs G quads per thread back to back so the BatchNorm statistics of the
 // result are carried in registers and reduced (shuffles -> shared -> one double atomic per channel) once.
 #include "common.cuh"
+#include "conv_common.cuh"
 
 namespace seist {
 
@@ -528,56 +529,73 @@ int launch_res_bwd4(const SeistOp& op, cudaStream_t s, int sm_count) {
 }
 
 // ================================================================================================
-// backward (weights) for k = 1:  dW[co][ci] = sum_{n,l} gacc[co][n,l] * f(in[ci])[n,l]
+// backward (weights), groups == 1, any k / stride / up-sampled input:
+//   dW[co][r] = sum_{n,l} gacc[co][n,l] * convin[ci(r)][n, l*S + t(r) - pad_left],   r = ci*k + t
 //
-// A CTA owns a CO_B x CI_B tile of dW and a strided share of all 128-sample chunks.  Per chunk every
-// needed element is loaded (float4, all loads of the chunk in flight at once), transformed ONCE
-// (BN-backward prologue for gacc; BN-apply/GELU for the input) and parked in shared memory; the
-// threads then form TG = (CO_B/4)*(CI_B/8) tile coordinates x PG sample groups: each thread keeps a
-// 4 x 8 register tile and walks its sample quads with 16-byte shared loads (12 LDS.128 per 128 FMA).
-// Sample groups are folded through shared memory once at the end; one float atomic per dW element
-// per CTA.  dbias comes from the ci-tile-0 CTAs.
+// A CTA owns a CO_B x R_B tile of dW and a strided share of all 128-sample chunks.  Per chunk every
+// needed element is loaded (all loads of the chunk in flight at once), transformed ONCE (BN-backward
+// prologue for gacc; BN-apply / GELU / up-sampling / padding for the input) and parked in shared
+// memory; the threads then form TG = (CO_B/4)*(R_B/8) tile coordinates x PG sample groups: each thread
+// keeps a 4 x 8 register tile and walks its sample quads (k = 1: 12 LDS.128 per 128 FMA).  Sample groups
+// are folded through shared memory once at the end; one float atomic per dW element per CTA.
 // ================================================================================================
 constexpr int BW_NT = 256;
-constexpr int BW_PC = 128;            // samples per chunk
-constexpr int BW_PITCH = BW_PC + 4;   // row pitch (floats), keeps 16-byte alignment
+constexpr int BW_PC = 128;            // output samples per chunk
+constexpr int BW_PITCH = BW_PC + 4;   // gacc row pitch (floats), keeps 16-byte alignment
 
-template <int CO_B, int CI_B>
-__global__ void __launch_bounds__(BW_NT) pw_bwd_w_kernel(const __grid_constant__ SeistOp op) {
+template <int CO_B, int R_B, bool K1>
+__global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ SeistOp op, const int nci_max) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  constexpr int TGM = CO_B / 4, TGN = CI_B / 8, TG = TGM * TGN, PG = BW_NT / TG;
+  constexpr int TGM = CO_B / 4, TGN = R_B / 8, TG = TGM * TGN, PG = BW_NT / TG;
   static_assert(TG <= BW_NT && BW_NT % TG == 0, "bad tile");
-  float* g_s = reinterpret_cast<float*>(sm_raw);            // [CO_B][PITCH]
-  float* in_s = g_s + CO_B * BW_PITCH;                      // [CI_B][PITCH]
-  constexpr int STAGE_F = (CO_B + CI_B) * BW_PITCH > BW_NT * 36 ? (CO_B + CI_B) * BW_PITCH : BW_NT * 36;
-  PwChan* ch_s = reinterpret_cast<PwChan*>(g_s + STAGE_F);            // [CI_B], behind staging/reduction area
-  PwOut* oc_s = reinterpret_cast<PwOut*>(ch_s + CI_B);                // [CO_B]
-  const int tid = threadIdx.x;
-  const int co_base = blockIdx.y * CO_B, ci_base = blockIdx.z * CI_B;
-  const int Cin = op.Cin, Cout = op.Cout, L = op.L_out;
+  const int k = op.k, S = op.stride, Cin = op.Cin, Cout = op.Cout, L = op.L_out;
+  const int R = Cin * k;
+  const int width = BW_PC * S + k - S;
+  const int pitch = K1 ? BW_PITCH : (width | 1);            // odd pitch: scalar reads spread over banks
+  const int stage_f = CO_B * BW_PITCH + nci_max * pitch;
+  const int area_f = stage_f > BW_NT * 36 ? stage_f : BW_NT * 36;
+  float* g_s = reinterpret_cast<float*>(sm_raw);            // [CO_B][BW_PITCH]
+  float* in_s = g_s + CO_B * BW_PITCH;                      // [nci][pitch]
+  PwOut* oc_s = reinterpret_cast<PwOut*>(g_s + ((area_f + 3) & ~3));   // [CO_B]
+  PwChan* ch_s = reinterpret_cast<PwChan*>(oc_s + CO_B);                // [nci_max] (k = 1 fast path)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int co_base = blockIdx.y * CO_B, r_base = blockIdx.z * R_B;
+  const int ci_lo = r_base / k;
+  const int ci_hi = min((r_base + R_B - 1) / k, Cin - 1);
+  const int nci = ci_hi - ci_lo + 1;
 
-  for (int col = tid; col < CI_B; col += BW_NT) {
-    const int ci = ci_base + col;
-    ch_s[col] = make_chan(op, ci < Cin ? ci : 0, false);
-  }
   for (int col = tid; col < CO_B; col += BW_NT) {
     const int co = co_base + col;
     PwOut o = {0.f, 0.f, 0.f};
     if (co < Cout) {
-      const OutGradCoef k = out_grad_coef(op, co);
-      o.A = k.A;
-      o.Bx = k.Bx;
-      o.Cc = k.Cc;
+      const OutGradCoef kc = out_grad_coef(op, co);
+      o.A = kc.A;
+      o.Bx = kc.Bx;
+      o.Cc = kc.Cc;
     }
     oc_s[col] = o;
   }
+  if (K1)
+    for (int row = tid; row < nci; row += BW_NT) ch_s[row] = make_chan(op, ci_lo + row, false);
   __syncthreads();
 
   const uint64_t seed = load_seed(op.step_seed);
   const bool has_bn = (op.out.bn >= 0 && op.out.g != nullptr);
   const bool need_x = has_bn || op.out_act == SEIST_OUT_SIGMOID;
+  const bool vec = (L & 3) == 0;
+  const bool plain = op.pool <= 1 && op.up_src_L == 0;
+  const int Lsrc = op.in[0].L;
+  const float ratio = op.up_src_L > 0 ? (float)Lsrc / (float)op.L_in : 1.f;
   const int tcoord = tid % TG, pg = tid / TG;
   const int tm = tcoord / TGN, tn = tcoord % TGN;
+  int roff[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int r = r_base + tn * 8 + j;
+    const int rr = r < R ? r : r_base;            // padded columns read valid memory; never written back
+    const int ci = rr / k, t = rr - ci * k;
+    roff[j] = (ci - ci_lo) * pitch + t;
+  }
   float acc[4][8];
   float bacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -587,86 +605,141 @@ __global__ void __launch_bounds__(BW_NT) pw_bwd_w_kernel(const __grid_constant__
 
   const int chunks_per_n = (L + BW_PC - 1) / BW_PC;
   const int total = op.N * chunks_per_n;
-  constexpr int QPR = BW_PC / 4;                 // quads per row
+  constexpr int QPR = BW_PC / 4;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const int n = tile / chunks_per_n;
     const int l0 = (tile - n * chunks_per_n) * BW_PC;
     const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
-    // ---- stage gacc rows ------------------------------------------------------------------------
-    for (int idx = tid; idx < CO_B * QPR; idx += BW_NT) {
-      const int row = idx / QPR, q = idx - row * QPR;
-      const int co = co_base + row, l = l0 + 4 * q;
-      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (co < Cout && l < L) {
-        const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l;
-        if (op.out_dxd) gv = ldg4(op.out_dxd + off);
-        if (need_x) {
-          const float4 x = ldg4(op.out.x + off);
-          if (has_bn) {
-            const float4 du = ldg4(op.out.g + off);
-            const PwOut o = oc_s[row];
-            gv.x += fmaf(o.A, du.x, fmaf(o.Bx, x.x, o.Cc));
-            gv.y += fmaf(o.A, du.y, fmaf(o.Bx, x.y, o.Cc));
-            gv.z += fmaf(o.A, du.z, fmaf(o.Bx, x.z, o.Cc));
-            gv.w += fmaf(o.A, du.w, fmaf(o.Bx, x.w, o.Cc));
+    // ---- gacc rows ------------------------------------------------------------------------------
+    if (vec) {
+      for (int idx = tid; idx < CO_B * QPR; idx += BW_NT) {
+        const int row = idx / QPR, q = idx - row * QPR;
+        const int co = co_base + row, l = l0 + 4 * q;
+        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (co < Cout && l < L) {
+          const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l;
+          if (op.out_dxd) gv = ldg4(op.out_dxd + off);
+          if (need_x) {
+            const float4 x = ldg4(op.out.x + off);
+            if (has_bn) {
+              const float4 du = ldg4(op.out.g + off);
+              const PwOut o = oc_s[row];
+              gv.x += fmaf(o.A, du.x, fmaf(o.Bx, x.x, o.Cc));
+              gv.y += fmaf(o.A, du.y, fmaf(o.Bx, x.y, o.Cc));
+              gv.z += fmaf(o.A, du.z, fmaf(o.Bx, x.z, o.Cc));
+              gv.w += fmaf(o.A, du.w, fmaf(o.Bx, x.w, o.Cc));
+            }
+            if (op.out_act == SEIST_OUT_SIGMOID) {
+              gv.x *= x.x * (1.f - x.x);
+              gv.y *= x.y * (1.f - x.y);
+              gv.z *= x.z * (1.f - x.z);
+              gv.w *= x.w * (1.f - x.w);
+            }
           }
-          if (op.out_act == SEIST_OUT_SIGMOID) {
-            gv.x *= x.x * (1.f - x.x);
-            gv.y *= x.y * (1.f - x.y);
-            gv.z *= x.z * (1.f - x.z);
-            gv.w *= x.w * (1.f - x.w);
+          gv.x *= pf;
+          gv.y *= pf;
+          gv.z *= pf;
+          gv.w *= pf;
+          if (op.p_elem > 0.f) {
+            const uint64_t e = ((uint64_t)n * Cout + co) * (uint64_t)L + l;
+            gv.x *= keep_scale(op.p_elem, seed, op.seed_elem, e);
+            gv.y *= keep_scale(op.p_elem, seed, op.seed_elem, e + 1);
+            gv.z *= keep_scale(op.p_elem, seed, op.seed_elem, e + 2);
+            gv.w *= keep_scale(op.p_elem, seed, op.seed_elem, e + 3);
           }
         }
-        gv.x *= pf;
-        gv.y *= pf;
-        gv.z *= pf;
-        gv.w *= pf;
-        if (op.p_elem > 0.f) {
-          const uint64_t e = ((uint64_t)n * Cout + co) * (uint64_t)L + l;
-          gv.x *= keep_scale(op.p_elem, seed, op.seed_elem, e);
-          gv.y *= keep_scale(op.p_elem, seed, op.seed_elem, e + 1);
-          gv.z *= keep_scale(op.p_elem, seed, op.seed_elem, e + 2);
-          gv.w *= keep_scale(op.p_elem, seed, op.seed_elem, e + 3);
-        }
+        st4(g_s + row * BW_PITCH + 4 * q, gv);
       }
-      st4(g_s + row * BW_PITCH + 4 * q, gv);
+    } else {
+      for (int idx = tid; idx < CO_B * BW_PC; idx += BW_NT) {
+        const int row = idx / BW_PC, pos = idx - row * BW_PC;
+        const int co = co_base + row, l = l0 + pos;
+        float v = 0.f;
+        if (co < Cout && l < L) {
+          OutGradCoef kc;
+          kc.A = oc_s[row].A;
+          kc.Bx = oc_s[row].Bx;
+          kc.Cc = oc_s[row].Cc;
+          v = out_grad_at(op, kc, n, co, l) * pf * elem_factor(op, seed, n, co, l);
+        }
+        g_s[row * BW_PITCH + pos] = v;
+      }
     }
-    // ---- stage input rows -------------------------------------------------------------------------
-    for (int idx = tid; idx < CI_B * QPR; idx += BW_NT) {
-      const int row = idx / QPR, q = idx - row * QPR;
-      const int ci = ci_base + row, l = l0 + 4 * q;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ci < Cin && l < L) {
-        const PwChan& c = ch_s[row];
-        v = apply_view(ldg4(c.x + (long long)n * c.nstride + l), c.sc, c.sh, c.act);
+    // ---- conv-input rows --------------------------------------------------------------------------
+    const int p_base = l0 * S - op.pad_left;
+    if (K1 && vec && plain) {
+      for (int idx = tid; idx < nci * QPR; idx += BW_NT) {
+        const int row = idx / QPR, q = idx - row * QPR;
+        const int l = l0 + 4 * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < L) {
+          const PwChan& c = ch_s[row];
+          v = apply_view(ldg4(c.x + (long long)n * c.nstride + l), c.sc, c.sh, c.act);
+        }
+        st4(in_s + row * pitch + 4 * q, v);
       }
-      st4(in_s + row * BW_PITCH + 4 * q, v);
+    } else {
+      for (int r = warp; r < nci; r += BW_NT / 32) {
+        const RowSrc rs = make_row(op, n, ci_lo + r);
+        float* dst = in_s + r * pitch;
+        if (plain) {
+          for (int pos0 = lane; pos0 < width; pos0 += 32 * 4) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int p = p_base + pos0 + 32 * u;
+              v[u] = (pos0 + 32 * u < width && p >= 0 && p < op.L_in) ? rs.x[p] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int pos = pos0 + 32 * u, p = p_base + pos;
+              if (pos < width) {
+                float t = fmaf(rs.sc, v[u], rs.sh);
+                if (rs.act == SEIST_ACT_GELU) t = gelu_f(t);
+                dst[pos] = (p >= 0 && p < op.L_in) ? t : 0.f;
+              }
+            }
+          }
+        } else {
+          for (int pos = lane; pos < width; pos += 32) dst[pos] = conv_input_at(op, rs, p_base + pos, Lsrc, ratio);
+        }
+      }
     }
     __syncthreads();
     // ---- accumulate ---------------------------------------------------------------------------------
     for (int q = pg; q < QPR; q += PG) {
-      float4 gq[4], iq[8];
+      float4 gq[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) gq[i] = ld4(g_s + (tm * 4 + i) * BW_PITCH + 4 * q);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) iq[j] = ld4(in_s + (tn * 8 + j) * BW_PITCH + 4 * q);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[i][j] = fmaf(gq[i].x, iq[j].x, acc[i][j]);
-          acc[i][j] = fmaf(gq[i].y, iq[j].y, acc[i][j]);
-          acc[i][j] = fmaf(gq[i].z, iq[j].z, acc[i][j]);
-          acc[i][j] = fmaf(gq[i].w, iq[j].w, acc[i][j]);
+      for (int j = 0; j < 8; ++j) {
+        float4 iq;
+        if (K1) {
+          iq = ld4(in_s + roff[j] + 4 * q);
+        } else {
+          const float* ip = in_s + roff[j] + 4 * q * S;
+          iq = make_float4(ip[0], ip[S], ip[2 * S], ip[3 * S]);
         }
-        if (tn == 0) bacc[i] += (gq[i].x + gq[i].y) + (gq[i].z + gq[i].w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float a = acc[i][j];
+          a = fmaf(gq[i].x, iq.x, a);
+          a = fmaf(gq[i].y, iq.y, a);
+          a = fmaf(gq[i].z, iq.z, a);
+          a = fmaf(gq[i].w, iq.w, a);
+          acc[i][j] = a;
+        }
+      }
+      if (tn == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bacc[i] += (gq[i].x + gq[i].y) + (gq[i].z + gq[i].w);
       }
     }
     __syncthreads();
   }
 
   // ---- fold the sample groups through shared memory (reuses the staging area) -------------------------
-  float* red = g_s;                                  // [PG][TG][36] needs PG*TG*36 = 256*36 floats = 36 KB max
+  float* red = g_s;
   constexpr int RW = 36;
   float* mine = red + (size_t)tid * RW;
 #pragma unroll
@@ -682,8 +755,8 @@ __global__ void __launch_bounds__(BW_NT) pw_bwd_w_kernel(const __grid_constant__
     for (int p = 0; p < PG; ++p) s += red[((size_t)p * TG + tc) * RW + e];
     const int m = tc / TGN, nn = tc % TGN;
     if (e < 32) {
-      const int co = co_base + m * 4 + (e >> 3), ci = ci_base + nn * 8 + (e & 7);
-      if (co < Cout && ci < Cin) atomicAdd(&op.dW[(size_t)co * Cin + ci], s);
+      const int co = co_base + m * 4 + (e >> 3), r = r_base + nn * 8 + (e & 7);
+      if (co < Cout && r < R) atomicAdd(&op.dW[(size_t)co * R + r], s);
     } else if (nn == 0 && blockIdx.z == 0 && op.dbias != nullptr) {
       const int co = co_base + m * 4 + (e - 32);
       if (co < Cout) atomicAdd(&op.dbias[co], s);
@@ -691,42 +764,60 @@ __global__ void __launch_bounds__(BW_NT) pw_bwd_w_kernel(const __grid_constant__
   }
 }
 
-template <int CO_B, int CI_B>
+template <int CO_B, int R_B, bool K1>
 static int launch_bww(const SeistOp& op, cudaStream_t s, int sm_count) {
-  size_t stage = sizeof(float) * (size_t)(CO_B + CI_B) * BW_PITCH;
-  const size_t red = sizeof(float) * (size_t)BW_NT * 36;
-  if (stage < red) stage = red;
-  const size_t smem = stage + sizeof(PwChan) * CI_B + sizeof(PwOut) * CO_B + 64;
-  // note: ch_s/oc_s are placed after the staging rows; keep the staging area >= the reduction area
-  const int gy = (op.Cout + CO_B - 1) / CO_B, gz = (op.Cin + CI_B - 1) / CI_B;
+  const int k = op.k, S = op.stride;
+  int nci_max = (R_B + k - 1) / k + 1;
+  if (nci_max > op.Cin) nci_max = op.Cin;
+  const int width = BW_PC * S + k - S;
+  const int pitch = K1 ? BW_PITCH : (width | 1);
+  int stage_f = CO_B * BW_PITCH + nci_max * pitch;
+  if (stage_f < BW_NT * 36) stage_f = BW_NT * 36;
+  const size_t smem = sizeof(float) * (size_t)((stage_f + 3) & ~3) + sizeof(PwOut) * CO_B + sizeof(PwChan) * (nci_max + 1) + 64;
+  const int R = op.Cin * k;
+  const int gy = (op.Cout + CO_B - 1) / CO_B, gz = (R + R_B - 1) / R_B;
   const long tiles = (long)op.N * ((op.L_out + BW_PC - 1) / BW_PC);
   long gx = (2L * sm_count + gy * gz - 1) / (gy * gz);
   if (gx > tiles) gx = tiles;
   if (gx < 1) gx = 1;
-  int rc = pw_set_smem(pw_bwd_w_kernel<CO_B, CI_B>, smem);
+  int rc = pw_set_smem(bww_kernel<CO_B, R_B, K1>, smem);
   if (rc) return rc;
-  pw_bwd_w_kernel<CO_B, CI_B><<<dim3((unsigned)gx, gy, gz), BW_NT, smem, s>>>(op);
+  bww_kernel<CO_B, R_B, K1><<<dim3((unsigned)gx, gy, gz), BW_NT, smem, s>>>(op, nci_max);
   note_launch();
-  return check_launch("pw_bwd_w");
+  return check_launch("bww");
 }
 
-int launch_pw_bwd_w(const SeistOp& op, cudaStream_t s, int sm_count) {
-  const int co = op.Cout, ci = op.Cin;
+template <bool K1>
+static int launch_bww_sel(const SeistOp& op, cudaStream_t s, int sm_count) {
+  const int co = op.Cout, R = op.Cin * op.k;
   if (co <= 8) {
-    if (ci <= 8) return launch_bww<8, 8>(op, s, sm_count);
-    if (ci <= 16) return launch_bww<8, 16>(op, s, sm_count);
-    return launch_bww<8, 32>(op, s, sm_count);
+    if (R <= 8) return launch_bww<8, 8, K1>(op, s, sm_count);
+    if (R <= 16) return launch_bww<8, 16, K1>(op, s, sm_count);
+    if (R <= 32) return launch_bww<8, 32, K1>(op, s, sm_count);
+    return launch_bww<8, 64, K1>(op, s, sm_count);
   }
   if (co <= 16) {
-    if (ci <= 8) return launch_bww<16, 8>(op, s, sm_count);
-    if (ci <= 16) return launch_bww<16, 16>(op, s, sm_count);
-    if (ci <= 32) return launch_bww<16, 32>(op, s, sm_count);
-    return launch_bww<16, 64>(op, s, sm_count);
+    if (R <= 8) return launch_bww<16, 8, K1>(op, s, sm_count);
+    if (R <= 16) return launch_bww<16, 16, K1>(op, s, sm_count);
+    if (R <= 32) return launch_bww<16, 32, K1>(op, s, sm_count);
+    return launch_bww<16, 64, K1>(op, s, sm_count);
   }
-  if (ci <= 8) return launch_bww<32, 8>(op, s, sm_count);
-  if (ci <= 16) return launch_bww<32, 16>(op, s, sm_count);
-  if (ci <= 32) return launch_bww<32, 32>(op, s, sm_count);
-  return launch_bww<32, 64>(op, s, sm_count);
+  if (R <= 8) return launch_bww<32, 8, K1>(op, s, sm_count);
+  if (R <= 16) return launch_bww<32, 16, K1>(op, s, sm_count);
+  if (R <= 32) return launch_bww<32, 32, K1>(op, s, sm_count);
+  return launch_bww<32, 64, K1>(op, s, sm_count);
+}
+
+// eligibility: dense (groups == 1), single input view unless k == 1, no pooling
+bool bww_eligible(const SeistOp& op) {
+  if (op.groups != 1 || op.pool > 1) return false;
+  if (op.k > 1 && op.n_in != 1) return false;
+  return true;
+}
+
+int launch_bww_any(const SeistOp& op, cudaStream_t s, int sm_count) {
+  if (op.k == 1 && op.stride == 1) return launch_bww_sel<true>(op, s, sm_count);
+  return launch_bww_sel<false>(op, s, sm_count);
 }
 
 }  // namespace seist
