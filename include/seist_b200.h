@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIST_ABI_VERSION 5
+#define SEIST_ABI_VERSION 6
 #define SEIST_MAX_IN 3
 
 /* ---- BatchNorm table entry (nn.BatchNorm1d, models/seist.py:641) ---------------- */
@@ -167,6 +167,11 @@ uint64_t seist_launch_count(void);
 
 /* run ops[0..n) in order on `stream` */
 int seist_plan_run(const SeistOp* ops, int32_t n, void* stream);
+/* same, but the weight-gradient ops (CONV_BWD_W, STEM_COMPOSE_BWD) — which nothing in the backward chain
+   depends on — are issued on `side_stream`, ordered after the preceding ops of `stream` with events and
+   joined back into `stream` before returning (fork/join, CUDA-graph capturable).  side_stream == NULL
+   behaves like seist_plan_run. */
+int seist_plan_run2(const SeistOp* ops, int32_t n, void* stream, void* side_stream);
 
 /* BCELoss(weight) with eps inside the logs — models/loss.py:48-56.  preds/targets (N,C,L);
    weight [C]; loss_sum: device double accumulator (zeroed by the call); *loss_out = sum / numel. */

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libseist_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_IN = 3
 
 
@@ -80,6 +80,8 @@ def lib():
     L.seist_launch_count.restype = C.c_uint64
     L.seist_plan_run.restype = C.c_int
     L.seist_plan_run.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.seist_plan_run2.restype = C.c_int
+    L.seist_plan_run2.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.seist_bce_fwd.restype = C.c_int
     L.seist_bce_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,
                                 C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -110,7 +112,7 @@ def lib():
 
 EXPORTS = [
     "seist_abi_version", "seist_sizeof_op", "seist_sizeof_bn", "seist_last_error", "seist_launch_count",
-    "seist_plan_run", "seist_bce_fwd", "seist_bce_bwd", "seist_huber_fwd", "seist_huber_bwd",
+    "seist_plan_run", "seist_plan_run2", "seist_bce_fwd", "seist_bce_bwd", "seist_huber_fwd", "seist_huber_bwd",
     "seist_adam_step", "seist_advance_seed",
 ]
 

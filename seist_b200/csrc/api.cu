@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 #include "common.cuh"
 
 namespace seist {
@@ -98,11 +99,61 @@ static int run_one(const SeistOp& op, cudaStream_t s) {
 
 extern "C" {
 
+int seist_plan_run(const SeistOp* ops, int32_t n, void* stream);
+
 int seist_abi_version(void) { return SEIST_ABI_VERSION; }
 uint64_t seist_sizeof_op(void) { return sizeof(SeistOp); }
 uint64_t seist_sizeof_bn(void) { return sizeof(SeistBN); }
 const char* seist_last_error(void) { return seist::g_err; }
 uint64_t seist_launch_count(void) { return seist::g_launches.load(); }
+
+static std::vector<cudaEvent_t> g_events;
+static cudaEvent_t event_at(size_t i) {
+  while (g_events.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    g_events.push_back(e);
+  }
+  return g_events[i];
+}
+
+int seist_plan_run2(const SeistOp* ops, int32_t n, void* stream, void* side_stream) {
+  if (side_stream == nullptr || side_stream == stream) return seist_plan_run(ops, n, stream);
+  if (ops == nullptr || n < 0) { seist::set_error("plan_run2: bad arguments"); return -1; }
+  cudaStream_t s = (cudaStream_t)stream, side = (cudaStream_t)side_stream;
+  size_t ev = 0;
+  bool forked = false, main_dirty = true;
+  for (int i = 0; i < n; ++i) {
+    const bool on_side = ops[i].kind == SEIST_OP_CONV_BWD_W || ops[i].kind == SEIST_OP_STEM_COMPOSE_BWD;
+    int rc;
+    if (on_side) {
+      if (main_dirty) {      // order after everything issued on the main stream so far
+        cudaEvent_t e = event_at(ev++);
+        cudaEventRecord(e, s);
+        cudaStreamWaitEvent(side, e, 0);
+        main_dirty = false;
+      }
+      rc = seist::run_one(ops[i], side);
+      forked = true;
+    } else {
+      rc = seist::run_one(ops[i], s);
+      main_dirty = true;
+    }
+    if (rc != 0) {
+      char buf[600];
+      std::snprintf(buf, sizeof(buf), "op %d (kind %d): %s", i, ops[i].kind, seist::g_err);
+      seist::set_error(buf);
+      if (forked) { cudaEvent_t e = event_at(ev++); cudaEventRecord(e, side); cudaStreamWaitEvent(s, e, 0); }
+      return rc;
+    }
+  }
+  if (forked) {
+    cudaEvent_t e = event_at(ev++);
+    cudaEventRecord(e, side);
+    cudaStreamWaitEvent(s, e, 0);
+  }
+  return 0;
+}
 
 int seist_plan_run(const SeistOp* ops, int32_t n, void* stream) {
   if (ops == nullptr || n < 0) { seist::set_error("plan_run: bad arguments"); return -1; }

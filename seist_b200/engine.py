@@ -47,6 +47,8 @@ class Engine:
         self.plans: Dict[Tuple, P.Plan] = {}
         self._trigger = None
         self.last_plan: Optional[P.Plan] = None
+        self.overlap_bwd_w = True
+        self._side = {}
 
     # ---- lifecycle -------------------------------------------------------------------------------
     def invalidate(self, release_flat: bool = False):
@@ -84,15 +86,25 @@ class Engine:
         return pl
 
     # ---- execution -------------------------------------------------------------------------------
-    def _run_segments(self, plan: P.Plan, c_ops, segs, stat: torch.Tensor):
+    def _side_stream(self, device) -> int:
+        """Second stream for the weight-gradient ops of the backward plan (fork/join inside plan_run2)."""
+        if not self.overlap_bwd_w:
+            return 0
+        st = self._side.get(device)
+        if st is None:
+            st = self._side[device] = torch.cuda.Stream(device=device)
+        return st.cuda_stream
+
+    def _run_segments(self, plan: P.Plan, c_ops, segs, stat: torch.Tensor, side: bool = False):
         lib = _lib.lib()
         base = ctypes.addressof(c_ops)
         size = ctypes.sizeof(_lib.SeistOp)
+        side_ptr = self._side_stream(plan.device) if side else 0
         for start, end, sync in segs:
             for b in sync:
                 e = plan.bns[b]
                 dist.all_reduce(stat[e.st_off:e.st_off + 2 * e.C])
-            _lib.check(lib.seist_plan_run(base + start * size, end - start, _stream_ptr()), "seist_plan_run")
+            _lib.check(lib.seist_plan_run2(base + start * size, end - start, _stream_ptr(), side_ptr), "seist_plan_run")
 
     def run_forward(self, plan: P.Plan, x: torch.Tensor) -> torch.Tensor:
         plan.x_in.x.copy_(x)
@@ -114,7 +126,7 @@ class Engine:
         plan.gstat.zero_()
         plan.dWx.zero_()
         plan.y_out.dxd.copy_(dy.reshape(plan.y_out.dxd.shape))
-        self._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat)
+        self._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat, side=True)
         for name, p in self._named:
             if p.grad is None:
                 p.grad = flat.grad_view(name)

@@ -114,7 +114,7 @@ class Trainer:
         flat.G.zero_()
         plan.gstat.zero_()
         plan.dWx.zero_()
-        eng._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat)
+        eng._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat, side=True)
         gscale = 1.0
         if self.world > 1:
             dist.all_reduce(flat.G)            # one collective for all 1.5 MB of gradients (C1)
