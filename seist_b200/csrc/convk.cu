@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant_
   float* in_s = ck_smem;                               // [CIC][pitch]
   float* w_s = ck_smem + CK_CIC * pitch;               // [CIC][K][CO_B]
   float* red_s = w_s + CK_CIC * K * CO_B;              // [8 warps][16]
+  float* src_s = red_s + 8 * 16;                       // [CIC][width+4] (up-sampled input only)
   const int Lsrc = op.in[0].L;
   const float ratio = op.up_src_L > 0 ? (float)Lsrc / (float)op.L_in : 1.f;
   const int p_base = l0 * S - op.pad_left;
@@ -114,7 +115,13 @@ __global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant_
 
   for (int ci0 = 0; ci0 < op.Cin; ci0 += CK_CIC) {
     const int cic = min(CK_CIC, op.Cin - ci0);
-    ck_stage_input(op, n, ci0, cic, in_s, pitch, width, p_base, Lsrc, ratio);
+    if (op.up_src_L > 0) {
+      stage_upsampled_rows(op, n, ci0, cic, in_s, pitch, width, p_base, src_s, width + 4, Lsrc, ratio);
+      for (int r = cic + warp; r < CK_CIC; r += CK_NT / 32)
+        for (int pos = lane; pos < width; pos += 32) in_s[r * pitch + pos] = 0.f;
+    } else {
+      ck_stage_input(op, n, ci0, cic, in_s, pitch, width, p_base, Lsrc, ratio);
+    }
     for (int idx = tid; idx < CK_CIC * K * CO_B; idx += CK_NT) {
       const int col = idx % CO_B, rest = idx / CO_B;
       const int t = rest % K, r = rest / K;
@@ -343,150 +350,6 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
 }
 
 // ================================================================================================
-// backward (weights): dW[co][ci][t] = sum_{n,l} gacc[co][l] * convin[ci][l*S + t - pad_left]
-// warp (wm, wn) owns co in [4*wm, 4*wm+4) x ci in [TCI*wn, TCI*(wn+1)) x all K taps; lanes = sample quads
-// ================================================================================================
-template <int K, int S, int TCI>
-__global__ void __launch_bounds__(CK_NT) convk_bwd_w_kernel(const __grid_constant__ SeistOp op, const int WM) {
-  extern __shared__ __align__(16) float ck_smem[];
-  constexpr int PCW = 128;                               // output samples per chunk (one quad per lane)
-  constexpr int NV = CkWin<K, S>::NV;
-  const int WN = 8 / WM, CO_B = 4 * WM, CI_B = TCI * WN;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp % WM, wn = warp / WM;
-  const int co_base = blockIdx.y * CO_B, ci_base = blockIdx.z * CI_B;
-  const int width = PCW * S + K - S;
-  const int pitch = ((width + 3) & ~3) + 4;
-  constexpr int GPITCH = PCW + 4;
-  float* g_s = ck_smem;                                  // [CO_B][GPITCH]
-  float* in_s = ck_smem + CO_B * GPITCH;                 // [CI_B][pitch]
-  const uint64_t seed = load_seed(op.step_seed);
-  const int Lsrc = op.in[0].L;
-  const float ratio = op.up_src_L > 0 ? (float)Lsrc / (float)op.L_in : 1.f;
-  const bool plain = op.up_src_L == 0;
-
-  float acc[4][TCI][K];
-  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int c = 0; c < TCI; ++c)
-#pragma unroll
-      for (int t = 0; t < K; ++t) acc[i][c][t] = 0.f;
-
-  const int chunks_per_n = (op.L_out + PCW - 1) / PCW;
-  const int total = op.N * chunks_per_n;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int n = tile / chunks_per_n;
-    const int l0 = (tile - n * chunks_per_n) * PCW;
-    const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
-    // gacc rows
-    for (int r = warp; r < CO_B; r += CK_NT / 32) {
-      const int co = co_base + r;
-      float v[4];
-      OutGradCoef kc = {0.f, 0.f, 0.f};
-      if (co < op.Cout) kc = out_grad_coef(op, co);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int l = l0 + lane + 32 * u;
-        v[u] = (co < op.Cout && l < op.L_out) ? out_grad_at(op, kc, n, co, l) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int l = l0 + lane + 32 * u;
-        float t = v[u] * pf;
-        if (op.p_elem > 0.f && co < op.Cout && l < op.L_out) t *= elem_factor(op, seed, n, co, l);
-        g_s[r * GPITCH + lane + 32 * u] = t;
-      }
-    }
-    // conv-input rows
-    const int p_base = l0 * S - op.pad_left;
-    for (int r = warp; r < CI_B; r += CK_NT / 32) {
-      const int ci = ci_base + r;
-      float* dst = in_s + r * pitch;
-      if (ci >= op.Cin) {
-        for (int pos = lane; pos < width; pos += 32) dst[pos] = 0.f;
-        continue;
-      }
-      const RowSrc rs = make_row(op, n, ci);
-      if (plain) {
-        for (int pos0 = lane; pos0 < width; pos0 += 32 * 4) {
-          float v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int p = p_base + pos0 + 32 * u;
-            v[u] = (pos0 + 32 * u < width && p >= 0 && p < op.L_in) ? rs.x[p] : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int pos = pos0 + 32 * u, p = p_base + pos;
-            if (pos < width) {
-              float t = fmaf(rs.sc, v[u], rs.sh);
-              if (rs.act == SEIST_ACT_GELU) t = gelu_f(t);
-              dst[pos] = (p >= 0 && p < op.L_in) ? t : 0.f;
-            }
-          }
-        }
-      } else {
-        for (int pos = lane; pos < width; pos += 32) dst[pos] = conv_input_at(op, rs, p_base + pos, Lsrc, ratio);
-      }
-    }
-    __syncthreads();
-    {
-      float4 gq[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) gq[i] = lds4(g_s + (wm * 4 + i) * GPITCH + 4 * lane);
-#pragma unroll
-      for (int c = 0; c < TCI; ++c) {
-        const float* irow = in_s + (wn * TCI + c) * pitch + 4 * lane * S;
-        float win[NV * 4];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const float4 q = lds4(irow + 4 * v);
-          win[4 * v] = q.x;
-          win[4 * v + 1] = q.y;
-          win[4 * v + 2] = q.z;
-          win[4 * v + 3] = q.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int t = 0; t < K; ++t) {
-            float a = acc[i][c][t];
-            a = fmaf(gq[i].x, win[t], a);
-            a = fmaf(gq[i].y, win[S + t], a);
-            a = fmaf(gq[i].z, win[2 * S + t], a);
-            a = fmaf(gq[i].w, win[3 * S + t], a);
-            acc[i][c][t] = a;
-          }
-      }
-      if (wn == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) bacc[i] += (gq[i].x + gq[i].y) + (gq[i].z + gq[i].w);
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int co = co_base + wm * 4 + i;
-#pragma unroll
-    for (int c = 0; c < TCI; ++c) {
-      const int ci = ci_base + wn * TCI + c;
-#pragma unroll
-      for (int t = 0; t < K; ++t) {
-        const float s = warp_sum(acc[i][c][t]);
-        if (lane == 0 && co < op.Cout && ci < op.Cin) atomicAdd(&op.dW[((size_t)co * op.Cin + ci) * K + t], s);
-      }
-    }
-    if (wn == 0 && blockIdx.z == 0 && op.dbias != nullptr) {
-      const float s = warp_sum(bacc[i]);
-      if (lane == 0 && co < op.Cout) atomicAdd(&op.dbias[co], s);
-    }
-  }
-}
-
-// ================================================================================================
 // launchers
 // ================================================================================================
 bool convk_eligible(const SeistOp& op) {
@@ -515,7 +378,8 @@ template <int K, int S>
 static int launch_fwd_ks(const SeistOp& op, cudaStream_t s) {
   const int WC = pick_wc(op.Cout), WP = 8 / WC, CO_B = 8 * WC, TLo = 128 * WP;
   const int width = TLo * S + K - S, pitch = ((width + 3) & ~3) + 4;
-  const size_t smem = sizeof(float) * ((size_t)CK_CIC * pitch + (size_t)CK_CIC * K * CO_B + 8 * 16);
+  const size_t smem = sizeof(float) * ((size_t)CK_CIC * pitch + (size_t)CK_CIC * K * CO_B + 8 * 16 +
+                                       (op.up_src_L > 0 ? (size_t)CK_CIC * (width + 4) : 0));
   dim3 grid((op.L_out + TLo - 1) / TLo, op.N, (op.Cout + CO_B - 1) / CO_B);
   int rc = ck_set_smem(convk_fwd_kernel<K, S>, smem);
   if (rc) return rc;
@@ -535,25 +399,6 @@ static int launch_bwdd_k(const SeistOp& op, cudaStream_t s) {
   convk_bwd_data_kernel<K><<<grid, CK_NT, smem, s>>>(op, WC);
   note_launch();
   return check_launch("convk_bwd_data");
-}
-
-template <int K, int S, int TCI>
-static int launch_bwdw_ks(const SeistOp& op, cudaStream_t s, int sm_count) {
-  // warp grid: WM co-tiles (4 channels) x WN ci-tiles (TCI channels)
-  int WM = op.Cout > 16 ? 8 : (op.Cout > 8 ? 4 : (op.Cout > 4 ? 2 : 1));
-  const int WN = 8 / WM, CO_B = 4 * WM, CI_B = TCI * WN;
-  const int width = 128 * S + K - S, pitch = ((width + 3) & ~3) + 4;
-  const size_t smem = sizeof(float) * ((size_t)CO_B * 132 + (size_t)CI_B * pitch);
-  const int gy = (op.Cout + CO_B - 1) / CO_B, gz = (op.Cin + CI_B - 1) / CI_B;
-  const long tiles = (long)op.N * ((op.L_out + 127) / 128);
-  long gx = (3L * sm_count + gy * gz - 1) / (gy * gz);
-  if (gx > tiles) gx = tiles;
-  if (gx < 1) gx = 1;
-  int rc = ck_set_smem(convk_bwd_w_kernel<K, S, TCI>, smem);
-  if (rc) return rc;
-  convk_bwd_w_kernel<K, S, TCI><<<dim3((unsigned)gx, gy, gz), CK_NT, smem, s>>>(op, WM);
-  note_launch();
-  return check_launch("convk_bwd_w");
 }
 
 #define CK_SWITCH_K(FN, ...)              \
@@ -586,27 +431,6 @@ int launch_convk_bwd_data(const SeistOp& op, cudaStream_t s) {
 #define BD(KK, dummy) launch_bwdd_k<KK>(op, s)
   CK_SWITCH_K(BD, 0)
 #undef BD
-}
-
-int launch_convk_bwd_w(const SeistOp& op, cudaStream_t s, int sm_count) {
-  if (op.stride == 2) {
-    switch (op.k) {
-      case 7: return launch_bwdw_ks<7, 2, 4>(op, s, sm_count);
-      case 11: return launch_bwdw_ks<11, 2, 2>(op, s, sm_count);
-      case 15: return launch_bwdw_ks<15, 2, 1>(op, s, sm_count);
-      default: return launch_bwdw_ks<19, 2, 1>(op, s, sm_count);
-    }
-  }
-  switch (op.k) {
-    case 3: return launch_bwdw_ks<3, 1, 4>(op, s, sm_count);
-    case 5: return launch_bwdw_ks<5, 1, 4>(op, s, sm_count);
-    case 7: return launch_bwdw_ks<7, 1, 4>(op, s, sm_count);
-    case 9: return launch_bwdw_ks<9, 1, 2>(op, s, sm_count);
-    case 11: return launch_bwdw_ks<11, 1, 2>(op, s, sm_count);
-    case 13: return launch_bwdw_ks<13, 1, 1>(op, s, sm_count);
-    case 15: return launch_bwdw_ks<15, 1, 1>(op, s, sm_count);
-    default: return launch_bwdw_ks<19, 1, 1>(op, s, sm_count);
-  }
 }
 
 }  // namespace seist

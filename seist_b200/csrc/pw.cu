@@ -558,6 +558,7 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
   float* in_s = g_s + CO_B * BW_PITCH;                      // [nci][pitch]
   PwOut* oc_s = reinterpret_cast<PwOut*>(g_s + ((area_f + 3) & ~3));   // [CO_B]
   PwChan* ch_s = reinterpret_cast<PwChan*>(oc_s + CO_B);                // [nci_max] (k = 1 fast path)
+  float* src_s = reinterpret_cast<float*>(ch_s + nci_max + 1);          // [nci_max][width+4] (up-sampled input only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int co_base = blockIdx.y * CO_B, r_base = blockIdx.z * R_B;
   const int ci_lo = r_base / k;
@@ -591,7 +592,7 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
   int roff[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int r = r_base + tn * 8 + j;
+    const int r = r_base + tn + TGN * j;          // interleaved columns: lanes of a warp read adjacent rows
     const int rr = r < R ? r : r_base;            // padded columns read valid memory; never written back
     const int ci = rr / k, t = rr - ci * k;
     roff[j] = (ci - ci_lo) * pitch + t;
@@ -679,6 +680,9 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
         st4(in_s + row * pitch + 4 * q, v);
       }
     } else {
+      if (op.up_src_L > 0) {
+        stage_upsampled_rows(op, n, ci_lo, nci, in_s, pitch, width, p_base, src_s, width + 4, Lsrc, ratio);
+      } else
       for (int r = warp; r < nci; r += BW_NT / 32) {
         const RowSrc rs = make_row(op, n, ci_lo + r);
         float* dst = in_s + r * pitch;
@@ -710,7 +714,7 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
     for (int q = pg; q < QPR; q += PG) {
       float4 gq[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) gq[i] = ld4(g_s + (tm * 4 + i) * BW_PITCH + 4 * q);
+      for (int i = 0; i < 4; ++i) gq[i] = ld4(g_s + (tm + TGM * i) * BW_PITCH + 4 * q);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 iq;
@@ -755,10 +759,10 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
     for (int p = 0; p < PG; ++p) s += red[((size_t)p * TG + tc) * RW + e];
     const int m = tc / TGN, nn = tc % TGN;
     if (e < 32) {
-      const int co = co_base + m * 4 + (e >> 3), r = r_base + nn * 8 + (e & 7);
+      const int co = co_base + m + TGM * (e >> 3), r = r_base + nn + TGN * (e & 7);
       if (co < Cout && r < R) atomicAdd(&op.dW[(size_t)co * R + r], s);
     } else if (nn == 0 && blockIdx.z == 0 && op.dbias != nullptr) {
-      const int co = co_base + m * 4 + (e - 32);
+      const int co = co_base + m + TGM * (e - 32);
       if (co < Cout) atomicAdd(&op.dbias[co], s);
     }
   }
@@ -773,7 +777,8 @@ static int launch_bww(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int pitch = K1 ? BW_PITCH : (width | 1);
   int stage_f = CO_B * BW_PITCH + nci_max * pitch;
   if (stage_f < BW_NT * 36) stage_f = BW_NT * 36;
-  const size_t smem = sizeof(float) * (size_t)((stage_f + 3) & ~3) + sizeof(PwOut) * CO_B + sizeof(PwChan) * (nci_max + 1) + 64;
+  const size_t smem = sizeof(float) * (size_t)((stage_f + 3) & ~3) + sizeof(PwOut) * CO_B + sizeof(PwChan) * (nci_max + 1) + 64 +
+                      (op.up_src_L > 0 ? sizeof(float) * (size_t)nci_max * (width + 4) : 0);
   const int R = op.Cin * k;
   const int gy = (op.Cout + CO_B - 1) / CO_B, gz = (R + R_B - 1) / R_B;
   const long tiles = (long)op.N * ((op.L_out + BW_PC - 1) / BW_PC);

@@ -101,9 +101,14 @@ class Engine:
         size = ctypes.sizeof(_lib.SeistOp)
         side_ptr = self._side_stream(plan.device) if side else 0
         for start, end, sync in segs:
-            for b in sync:
-                e = plan.bns[b]
-                dist.all_reduce(stat[e.st_off:e.st_off + 2 * e.C])
+            i = 0
+            while i < len(sync):          # BN entries registered consecutively own contiguous slots: one call
+                j = i
+                while j + 1 < len(sync) and sync[j + 1] == sync[j] + 1:
+                    j += 1
+                lo, hi = plan.bns[sync[i]], plan.bns[sync[j]]
+                dist.all_reduce(stat[lo.st_off:hi.st_off + 2 * hi.C])
+                i = j + 1
             _lib.check(lib.seist_plan_run2(base + start * size, end - start, _stream_ptr(), side_ptr), "seist_plan_run")
 
     def run_forward(self, plan: P.Plan, x: torch.Tensor) -> torch.Tensor:
