@@ -43,10 +43,6 @@ int launch_res_bwd4(const SeistOp& op, cudaStream_t s, int sm_count);
 bool bww_eligible(const SeistOp& op);
 int launch_bww_any(const SeistOp& op, cudaStream_t s, int sm_count);
 bool convk_eligible(const SeistOp& op);
-bool pw2_fwd_eligible(const SeistOp& op);
-bool pw2_bwd_eligible(const SeistOp& op);
-int launch_pw2_fwd(const SeistOp& op, cudaStream_t s, int sm_count);
-int launch_pw2_bwd_data(const SeistOp& op, cudaStream_t s, int sm_count);
 int launch_convk_fwd(const SeistOp& op, cudaStream_t s);
 int launch_convk_bwd_data(const SeistOp& op, cudaStream_t s);
 int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s);
@@ -74,8 +70,8 @@ static int validate_conv(const SeistOp& op) {
 
 static int run_one(const SeistOp& op, cudaStream_t s) {
   switch (op.kind) {
-    case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (pw2_fwd_eligible(op)) return launch_pw2_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
-    case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); if (v) return v; if (pw2_bwd_eligible(op)) return launch_pw2_bwd_data(op, s, sm_count()); return (convk_eligible(op) && op.stride == 1) ? launch_convk_bwd_data(op, s) : launch_conv_bwd_data(op, s); }
+    case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (pw_eligible(op)) return launch_pw_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
+    case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); if (v) return v; if (pw_eligible(op)) return launch_pw_bwd_data(op, s, sm_count()); return (convk_eligible(op) && op.stride == 1) ? launch_convk_bwd_data(op, s) : launch_conv_bwd_data(op, s); }
     case SEIST_OP_CONV_BWD_W: { int v = validate_conv(op); if (v) return v; return bww_eligible(op) ? launch_bww_any(op, s, sm_count()) : launch_conv_bwd_w(op, s, sm_count()); }
     case SEIST_OP_RES_BWD: return (op.L_out & 3) ? launch_res_bwd(op, s) : launch_res_bwd4(op, s, sm_count());
     case SEIST_OP_ATT_FWD: return launch_att_fwd(op, s);

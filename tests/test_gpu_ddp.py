@@ -1,0 +1,71 @@
+"""-m gpu (needs >= 2 GPUs, skipped otherwise): two NCCL ranks running the fused train step with SyncBatchNorm
+statistics exchanged at the plan's sync points must equal one rank on the concatenated batch."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ZERO = dict(path_drop_rate=0, attn_drop_rate=0, key_drop_rate=0, mlp_drop_rate=0, other_drop_rate=0)
+NAME, L, NB = "seist_s_dpk", 2048, 8
+
+
+def _setup_model():
+    from harness import randomize
+    from seist_b200.models import create_model
+    m = randomize(create_model(NAME, in_channels=3, in_samples=L), seed=5)
+    m.set_drop_rates(**ZERO)
+    return m
+
+
+def _step(model, x, t, steps=2):
+    from seist_b200.train import Trainer
+    tr = Trainer(model, lr=1e-3, use_graph=False)
+    losses = [float(tr.step(x, t).item()) for _ in range(steps)]
+    torch.cuda.synchronize()
+    return losses, tr
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle import seist_ref as R
+    x, t = R.synth_waveforms(NB, L, seed=3)
+    m = torch.nn.SyncBatchNorm.convert_sync_batchnorm(_setup_model().cuda())
+    n = NB // world
+    losses, tr = _step(m, x[rank * n:(rank + 1) * n].cuda(), t[rank * n:(rank + 1) * n].cuda())
+    lt = torch.tensor(losses, device="cuda")
+    dist.all_reduce(lt)
+    if rank == 0:
+        q.put(((lt / world).cpu(), tr.flat.P.detach().cpu().clone(), tr.flat.RB.cpu().clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpu_step_equals_single_gpu_on_concatenated_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    loss2, P2, RB2 = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    from oracle import seist_ref as R
+    x, t = R.synth_waveforms(NB, L, seed=3)
+    losses, tr = _step(_setup_model().cuda(), x.cuda(), t.cuda())
+    assert torch.allclose(loss2, torch.tensor(losses), rtol=1e-4, atol=1e-6), (loss2, losses)
+    P1 = tr.flat.P.detach().cpu()
+    # two Adam steps at lr 1e-3: parameters move by ~2e-3; the two runs must agree far inside that
+    assert (P2 - P1).abs().max().item() < 2e-4, (P2 - P1).abs().max().item()
+    assert (RB2 - tr.flat.RB.cpu()).abs().max().item() < 1e-3 * (tr.flat.RB.abs().max().item() + 1e-3)
