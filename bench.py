@@ -105,6 +105,15 @@ def cpu_reference_step_rate(model_name, batch, length, steps, warmup, threads):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else (NCCL banner, library prints) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -143,7 +152,7 @@ def main():
                                  "sample": f"{steps} train steps of {args.cpu_batch} waveforms "
                                            f"(oracle port of the reference step, dropout identity)"},
                 "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch.distributed as dist
@@ -253,7 +262,7 @@ def main():
                 "launches_per_step": trainer.launches_per_step, "cuda_graph": trainer.graph is not None,
                 "loss": loss_val, "clocks": clocks, "roofline": roofline, "step_roofline": step_roofline,
                 "cpu_baseline": cpu_baseline, "arena_gb": trainer.plan.arena_bytes / 1e9}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -164,6 +164,8 @@ uint64_t seist_sizeof_bn(void);
 const char* seist_last_error(void);
 /* number of kernel launches issued by this library since load (bench `gpu_launches`) */
 uint64_t seist_launch_count(void);
+/* 1 if a tensor-core kernel ever timed out waiting for its MMA completion barrier (bounded spin) */
+int seist_tc_error_flag(void);
 
 /* run ops[0..n) in order on `stream` */
 int seist_plan_run(const SeistOp* ops, int32_t n, void* stream);

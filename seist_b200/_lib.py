@@ -78,6 +78,7 @@ def lib():
     L.seist_sizeof_bn.restype = C.c_uint64
     L.seist_last_error.restype = C.c_char_p
     L.seist_launch_count.restype = C.c_uint64
+    L.seist_tc_error_flag.restype = C.c_int
     L.seist_plan_run.restype = C.c_int
     L.seist_plan_run.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     L.seist_plan_run2.restype = C.c_int
@@ -112,7 +113,7 @@ def lib():
 
 EXPORTS = [
     "seist_abi_version", "seist_sizeof_op", "seist_sizeof_bn", "seist_last_error", "seist_launch_count",
-    "seist_plan_run", "seist_plan_run2", "seist_bce_fwd", "seist_bce_bwd", "seist_huber_fwd", "seist_huber_bwd",
+    "seist_tc_error_flag", "seist_plan_run", "seist_plan_run2", "seist_bce_fwd", "seist_bce_bwd", "seist_huber_fwd", "seist_huber_bwd",
     "seist_adam_step", "seist_advance_seed",
 ]
 

@@ -1,6 +1,7 @@
 // C-ABI entry points and the plan executor (include/seist_b200.h).
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "common.cuh"
@@ -43,10 +44,20 @@ int launch_res_bwd4(const SeistOp& op, cudaStream_t s, int sm_count);
 bool bww_eligible(const SeistOp& op);
 int launch_bww_any(const SeistOp& op, cudaStream_t s, int sm_count);
 bool convk_eligible(const SeistOp& op);
+bool pw_tc_eligible(const SeistOp& op);
+int launch_pw_tc_fwd(const SeistOp& op, cudaStream_t s, int sm_count);
+int pw_tc_error_flag();
 int launch_convk_fwd(const SeistOp& op, cudaStream_t s);
 int launch_convk_bwd_data(const SeistOp& op, cudaStream_t s);
 int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s);
 int launch_stem_compose(const SeistOp& op, bool fwd, cudaStream_t s);
+
+// tensor-core (tcgen05) path for the 1x1 forward: on unless SEIST_TC=0
+static int use_tc() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("SEIST_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
 
 static int sm_count() {
   if (g_sm_count == 0) {
@@ -70,7 +81,7 @@ static int validate_conv(const SeistOp& op) {
 
 static int run_one(const SeistOp& op, cudaStream_t s) {
   switch (op.kind) {
-    case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (pw_eligible(op)) return launch_pw_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
+    case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (use_tc() && pw_tc_eligible(op)) return launch_pw_tc_fwd(op, s, sm_count()); if (pw_eligible(op)) return launch_pw_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
     case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); if (v) return v; if (pw_eligible(op)) return launch_pw_bwd_data(op, s, sm_count()); return (convk_eligible(op) && op.stride == 1) ? launch_convk_bwd_data(op, s) : launch_conv_bwd_data(op, s); }
     case SEIST_OP_CONV_BWD_W: { int v = validate_conv(op); if (v) return v; return bww_eligible(op) ? launch_bww_any(op, s, sm_count()) : launch_conv_bwd_w(op, s, sm_count()); }
     case SEIST_OP_RES_BWD: return (op.L_out & 3) ? launch_res_bwd(op, s) : launch_res_bwd4(op, s, sm_count());
@@ -105,6 +116,7 @@ uint64_t seist_sizeof_op(void) { return sizeof(SeistOp); }
 uint64_t seist_sizeof_bn(void) { return sizeof(SeistBN); }
 const char* seist_last_error(void) { return seist::g_err; }
 uint64_t seist_launch_count(void) { return seist::g_launches.load(); }
+int seist_tc_error_flag(void) { return seist::pw_tc_error_flag(); }
 
 static std::vector<cudaEvent_t> g_events;
 static cudaEvent_t event_at(size_t i) {

@@ -1,0 +1,306 @@
+// 1x1 convolution forward on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+//   out[co][p] = sum_ci W[co][ci] * f(in[ci][p])            (reference nn.Conv1d k=1, models/seist.py:86,107,...)
+//
+// GEMM view per 128-sample tile:  D[M = 128 samples][N = Cout] += A[M][K = Cin] * B[N][K]^T
+//   A = the consumer view (BatchNorm-apply / GELU evaluated ONCE per element by the staging threads), written
+//       to shared memory in the UMMA canonical MN-major SWIZZLE_128B layout (samples contiguous: the natural
+//       (channel, sample) tile of the NCL tensor, 16-byte vector stores, bank-conflict free);
+//   B = the weights, K-major INTERLEAVE (no swizzle) canonical layout;
+//   D = fp32 accumulators in tensor memory (TMEM): lane = sample, column = output channel.
+// Precision: kind::tf32 keeps 10 mantissa bits, the parity bar is 1e-3 against an fp32 CPU forward through
+// ~50 layers, so every operand is split hi + lo (hi = top 19 bits, lo = x - hi) and three MMAs are issued:
+// Ahi*Bhi + Alo*Bhi + Ahi*Blo (error ~2^-21).  One elected thread issues the MMAs and commits them to an
+// mbarrier; the four warps then read their 32 TMEM lanes with tcgen05.ld and run the usual epilogue (bias,
+// dropout, residuals, BatchNorm statistics) with one sample per lane, i.e. 128-byte coalesced stores.
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace seist {
+
+constexpr int TC_NT = 128;
+constexpr int TC_M = 128;            // samples per tile == UMMA M
+constexpr int TC_KC = 32;            // reduction channels per chunk (4 UMMA K-steps of 8 tf32)
+constexpr int TC_A_BYTES = (TC_KC / 8) * 4096;           // one precision part of the A chunk
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp::SmemDescriptor)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;            // 0 = no swizzle, 2 = SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_split(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+__device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int it = 0; it < (1 << 20) && !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+  return done != 0;
+}
+
+__device__ int g_tc_err_dev = 0;     // set if an mbarrier wait ever timed out (bounded spin: never hangs the GPU)
+
+__global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant__ SeistOp op, const int N_pad,
+                                                          const int tmem_cols) {
+  extern __shared__ __align__(16) unsigned char tc_raw[];
+  // carve-up (A parts need 1024-byte alignment for the 128B swizzle atoms)
+  unsigned char* a_hi = tc_raw + ((1024u - (tc_smem_u32(tc_raw) & 1023u)) & 1023u);
+  unsigned char* a_lo = a_hi + TC_A_BYTES;
+  unsigned char* b_hi = a_lo + TC_A_BYTES;
+  const int b_bytes = (TC_KC / 8) * N_pad * 32;
+  unsigned char* b_lo = b_hi + b_bytes;
+  float* ep_s = reinterpret_cast<float*>(b_lo + b_bytes);           // bias, a_sc, a_sh, b_sc, b_sh [5][Cout]
+  float* red_s = ep_s + 5 * op.Cout;                                // [2*Cout]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red_s + 2 * op.Cout + ((7 * op.Cout) & 1));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Cin = op.Cin, Cout = op.Cout, L = op.L_out;
+
+  for (int co = tid; co < Cout; co += TC_NT) {
+    float b = 0.f, asc = 1.f, ash = 0.f, bsc = 1.f, bsh = 0.f;
+    if (op.bias) b = op.bias[co];
+    if (op.res_a.C > 0) view_coef(op, op.res_a, co, asc, ash);
+    if (op.res_b.C > 0) view_coef(op, op.res_b, co, bsc, bsh);
+    ep_s[co] = b;
+    ep_s[Cout + co] = asc;
+    ep_s[2 * Cout + co] = ash;
+    ep_s[3 * Cout + co] = bsc;
+    ep_s[4 * Cout + co] = bsh;
+    red_s[2 * co] = 0.f;
+    red_s[2 * co + 1] = 0.f;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)),
+                 "r"((uint32_t)tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t bar_addr = tc_smem_u32(bar);
+  uint32_t parity = 0;
+
+  // instruction descriptor: D=f32, A=B=tf32, A MN-major, B K-major, N = N_pad, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(N_pad >> 3) << 17) |
+                         ((uint32_t)(TC_M >> 4) << 24);
+
+  const uint64_t seed = load_seed(op.step_seed);
+  const bool stats = (op.out.bn >= 0) && op.bn_table[op.out.bn >= 0 ? op.out.bn : 0].use_batch;
+  const int tiles_per_n = (L + TC_M - 1) / TC_M;
+  const int total = op.N * tiles_per_n;
+  bool failed = false;
+
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = tile / tiles_per_n;
+    const int l0 = (tile - n * tiles_per_n) * TC_M;
+    for (int k0 = 0; k0 < Cin; k0 += TC_KC) {
+      // ---- stage A: (channel, sample) chunk -> canonical MN-major SW128, hi and lo parts --------------
+      {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = tid + u * TC_NT;               // 32 channels x 32 quads
+          const int r = idx >> 5, q = idx & 31;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k0 + r < Cin && l0 + 4 * q < L) {
+            int cv;
+            const int vi = resolve_view(op, k0 + r, cv);
+            const SeistView& vw = op.in[vi];
+            v[u] = __ldg(reinterpret_cast<const float4*>(view_row(vw, n, cv) + l0 + 4 * q));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = tid + u * TC_NT;
+          const int r = idx >> 5, q = idx & 31;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k0 + r < Cin && l0 + 4 * q < L) {
+            int cv;
+            const int vi = resolve_view(op, k0 + r, cv);
+            const SeistView& vw = op.in[vi];
+            float sc, sh;
+            view_coef(op, vw, cv, sc, sh);
+            t.x = fmaf(sc, v[u].x, sh);
+            t.y = fmaf(sc, v[u].y, sh);
+            t.z = fmaf(sc, v[u].z, sh);
+            t.w = fmaf(sc, v[u].w, sh);
+            if (vw.act == SEIST_ACT_GELU) {
+              t.x = gelu_f(t.x);
+              t.y = gelu_f(t.y);
+              t.z = gelu_f(t.z);
+              t.w = gelu_f(t.w);
+            }
+          }
+          float4 hi, lo;
+          tc_split(t.x, hi.x, lo.x);
+          tc_split(t.y, hi.y, lo.y);
+          tc_split(t.z, hi.z, lo.z);
+          tc_split(t.w, hi.w, lo.w);
+          // element (sample = 4q + j, k = r): K-block r/8, MN atom q/8, row r%8, 16-byte chunk (q%8) ^ (r%8)
+          const int off = (r >> 3) * 4096 + (q >> 3) * 1024 + (r & 7) * 128 + (((q & 7) ^ (r & 7)) << 4);
+          *reinterpret_cast<float4*>(a_hi + off) = hi;
+          *reinterpret_cast<float4*>(a_lo + off) = lo;
+        }
+      }
+      // ---- stage B: weights chunk -> canonical K-major (no swizzle), hi and lo parts ---------------------
+      for (int idx = tid; idx < N_pad * TC_KC; idx += TC_NT) {
+        const int k = idx % TC_KC, nn = idx / TC_KC;
+        float w = 0.f;
+        if (nn < Cout && k0 + k < Cin) w = op.W[(size_t)nn * Cin + k0 + k];
+        float hi, lo;
+        tc_split(w, hi, lo);
+        const int off = (k >> 3) * (N_pad * 32) + (nn >> 3) * 256 + ((k & 7) >> 2) * 128 + (nn & 7) * 16 + (k & 3) * 4;
+        *reinterpret_cast<float*>(b_hi + off) = hi;
+        *reinterpret_cast<float*>(b_lo + off) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (tensor core)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi_u = tc_smem_u32(a_hi), a_lo_u = tc_smem_u32(a_lo);
+        const uint32_t b_hi_u = tc_smem_u32(b_hi), b_lo_u = tc_smem_u32(b_lo);
+#pragma unroll
+        for (int kb = 0; kb < TC_KC / 8; ++kb) {
+          const uint64_t ah = tc_desc(a_hi_u + kb * 4096, 1024, 4096, 2);
+          const uint64_t al = tc_desc(a_lo_u + kb * 4096, 1024, 4096, 2);
+          const uint64_t bh = tc_desc(b_hi_u + kb * N_pad * 32, 128, 256, 0);
+          const uint64_t bl = tc_desc(b_lo_u + kb * N_pad * 32, 128, 256, 0);
+          tc_mma_tf32(tmem_base, ah, bh, idesc, (k0 > 0 || kb > 0) ? 1u : 0u);
+          tc_mma_tf32(tmem_base, al, bh, idesc, 1u);
+          tc_mma_tf32(tmem_base, ah, bl, idesc, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr)
+                     : "memory");
+      }
+      if (!tc_wait(bar_addr, parity)) failed = true;
+      parity ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+
+    // ---- epilogue: lane = sample (TMEM lane 32*warp + lane), 16 output channels per tcgen05.ld -------------
+    const int l = l0 + 32 * warp + lane;
+    const bool ok = l < L;
+    const float pf = path_factor(op, seed, n), af = alpha_factor(op, seed, n);
+    for (int c0 = 0; c0 < Cout; c0 += 16) {
+      uint32_t rr[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]),
+            "=r"(rr[8]), "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int co = c0 + c;
+        if (co >= Cout) break;
+        float s1 = 0.f, s2 = 0.f;
+        if (ok) {
+          float v = (__uint_as_float(rr[c]) + ep_s[co]) * pf * elem_factor(op, seed, n, co, l);
+          if (op.res_a.C > 0) v += fmaf(ep_s[Cout + co], view_row(op.res_a, n, co)[l], ep_s[2 * Cout + co]);
+          v *= af;
+          if (op.res_b.C > 0) v += fmaf(ep_s[3 * Cout + co], view_row(op.res_b, n, co)[l], ep_s[4 * Cout + co]);
+          if (op.out_act == SEIST_OUT_SIGMOID) v = sigmoid_f(v);
+          op.out.x[((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l] = v;
+          s1 = v;
+          s2 = v * v;
+        }
+        if (stats) {
+          s1 = warp_sum(s1);
+          s2 = warp_sum(s2);
+          if (lane == 0) {
+            atomicAdd(&red_s[2 * co], s1);
+            atomicAdd(&red_s[2 * co + 1], s2);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();       // all TMEM reads of this tile are done before the next tile's MMAs overwrite it
+  }
+
+  if (stats) {
+    __syncthreads();
+    const SeistBN& e = op.bn_table[op.out.bn];
+    for (int i = tid; i < 2 * Cout; i += TC_NT)
+      atomicAdd(&e.stat[(i & 1) * e.C + op.out.bn_c0 + (i >> 1)], (double)red_s[i]);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
+  }
+  if (failed) atomicExch(&g_tc_err_dev, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+bool pw_tc_eligible(const SeistOp& op) {
+  if (op.k != 1 || op.stride != 1 || op.groups != 1 || op.pool > 1 || op.up_src_L > 0) return false;
+  if ((op.L_out & 3) || op.Cout > 128 || op.Cout < 8) return false;
+  for (int i = 0; i < op.n_in; ++i)
+    if (op.in[i].L != op.L_out) return false;
+  return true;
+}
+
+int launch_pw_tc_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
+  const int N_pad = (op.Cout + 15) & ~15;
+  int cols = 32;
+  while (cols < N_pad) cols <<= 1;
+  const size_t smem = 2 * (size_t)TC_A_BYTES + 2 * (size_t)(TC_KC / 8) * N_pad * 32 + sizeof(float) * (7 * (size_t)op.Cout + 2) +
+                      16 + 1024;
+  static size_t max_set = 0;
+  if (smem > max_set) {
+    cudaError_t e = cudaFuncSetAttribute(pw_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem < 49152 ? 49152 : smem));
+    if (e != cudaSuccess) return (int)e;
+    max_set = smem;
+  }
+  const long tiles = (long)op.N * ((op.L_out + TC_M - 1) / TC_M);
+  long g = 4L * sm_count;
+  if (g > tiles) g = tiles;
+  pw_tc_fwd_kernel<<<(unsigned)(g < 1 ? 1 : g), TC_NT, smem, s>>>(op, N_pad, cols);
+  note_launch();
+  return check_launch("pw_tc_fwd");
+}
+
+int pw_tc_error_flag() {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, g_tc_err_dev, sizeof(int));
+  return v;
+}
+
+}  // namespace seist
