@@ -68,23 +68,65 @@ __device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity) {
 
 __device__ int g_tc_err_dev = 0;     // set if an mbarrier wait ever timed out (bounded spin: never hangs the GPU)
 
+struct TcChan {          // reduction channel of the consumer view, resolved once per CTA
+  const float* x;        // row base for n = 0
+  long long nstride;
+  float sc, sh;
+  int act, pad;
+};
+
+// 16 values per lane -> lane l returns the warp-wide sum of value (l & 15)  (16 shuffles instead of 80)
+__device__ __forceinline__ float tc_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < half) {
+        const float send = up ? v[i] : v[i + half];
+        const float keep = up ? v[i + half] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+// which of the 16 values lane `lane` holds after tc_reduce16
+__device__ __forceinline__ int tc_reduce16_index(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
 __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant__ SeistOp op, const int N_pad,
-                                                          const int tmem_cols) {
+                                                          const int tmem_cols, const int b_resident) {
   extern __shared__ __align__(16) unsigned char tc_raw[];
-  // carve-up (A parts need 1024-byte alignment for the 128B swizzle atoms)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Cin = op.Cin, Cout = op.Cout, L = op.L_out;
+  const int nchunks = (Cin + TC_KC - 1) / TC_KC;
+  const int b_chunk_bytes = (TC_KC / 8) * N_pad * 32;          // one precision part of one K-chunk of B
+  // carve-up
   unsigned char* a_hi = tc_raw + ((1024u - (tc_smem_u32(tc_raw) & 1023u)) & 1023u);
   unsigned char* a_lo = a_hi + TC_A_BYTES;
   unsigned char* b_hi = a_lo + TC_A_BYTES;
-  const int b_bytes = (TC_KC / 8) * N_pad * 32;
-  unsigned char* b_lo = b_hi + b_bytes;
-  float* ep_s = reinterpret_cast<float*>(b_lo + b_bytes);           // bias, a_sc, a_sh, b_sc, b_sh [5][Cout]
-  float* red_s = ep_s + 5 * op.Cout;                                // [2*Cout]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(red_s + 2 * op.Cout + ((7 * op.Cout) & 1));
+  const int b_parts = b_resident ? nchunks : 1;
+  unsigned char* b_lo = b_hi + b_parts * b_chunk_bytes;
+  float* ep_s = reinterpret_cast<float*>(b_lo + b_parts * b_chunk_bytes);   // bias, a_sc, a_sh, b_sc, b_sh [5][Cout]
+  float* red_s = ep_s + 5 * Cout;                                            // [4 warps][2*Cout]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red_s + 8 * Cout + ((13 * Cout) & 1));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  TcChan* ch_s = reinterpret_cast<TcChan*>(bar + 2);                         // [Cin]
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Cin = op.Cin, Cout = op.Cout, L = op.L_out;
-
+  for (int ci = tid; ci < Cin; ci += TC_NT) {
+    int cv;
+    const int vi = resolve_view(op, ci, cv);
+    const SeistView& vw = op.in[vi];
+    TcChan c;
+    c.x = vw.x + (size_t)(vw.c0 + cv) * vw.L;
+    c.nstride = (long long)vw.Ct * vw.L;
+    view_coef(op, vw, cv, c.sc, c.sh);
+    c.act = vw.act;
+    c.pad = 0;
+    ch_s[ci] = c;
+  }
   for (int co = tid; co < Cout; co += TC_NT) {
     float b = 0.f, asc = 1.f, ash = 0.f, bsc = 1.f, bsh = 0.f;
     if (op.bias) b = op.bias[co];
@@ -95,9 +137,27 @@ __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant_
     ep_s[2 * Cout + co] = ash;
     ep_s[3 * Cout + co] = bsc;
     ep_s[4 * Cout + co] = bsh;
-    red_s[2 * co] = 0.f;
-    red_s[2 * co + 1] = 0.f;
   }
+  for (int i = tid; i < 8 * Cout; i += TC_NT) red_s[i] = 0.f;
+
+  // weights -> canonical K-major, hi / lo parts: [chunk][k/8][n/8][(k%8)/4][n%8][k%4]
+  auto stage_b = [&](int chunk, int slot) {
+    const int k0 = chunk * TC_KC;
+    for (int idx = tid; idx < N_pad * TC_KC; idx += TC_NT) {
+      const int k = idx % TC_KC, nn = idx / TC_KC;
+      float w = 0.f;
+      if (nn < Cout && k0 + k < Cin) w = op.W[(size_t)nn * Cin + k0 + k];
+      float hi, lo;
+      tc_split(w, hi, lo);
+      const int off = slot * b_chunk_bytes + (k >> 3) * (N_pad * 32) + (nn >> 3) * 256 + ((k & 7) >> 2) * 128 + (nn & 7) * 16 +
+                      (k & 3) * 4;
+      *reinterpret_cast<float*>(b_hi + off) = hi;
+      *reinterpret_cast<float*>(b_lo + off) = lo;
+    }
+  };
+  if (b_resident)
+    for (int c = 0; c < nchunks; ++c) stage_b(c, c);
+
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)),
                  "r"((uint32_t)tmem_cols)
@@ -114,146 +174,162 @@ __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t bar_addr = tc_smem_u32(bar);
   uint32_t parity = 0;
+  bool pending = false;         // an MMA batch has been committed and not yet waited for
+  bool failed = false;
 
   // instruction descriptor: D=f32, A=B=tf32, A and B K-major, N = N_pad, M = 128
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N_pad >> 3) << 17) |
-                         ((uint32_t)(TC_M >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N_pad >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
   const uint64_t seed = load_seed(op.step_seed);
   const bool stats = (op.out.bn >= 0) && op.bn_table[op.out.bn >= 0 ? op.out.bn : 0].use_batch;
   const int tiles_per_n = (L + TC_M - 1) / TC_M;
   const int total = op.N * tiles_per_n;
-  bool failed = false;
+  const int m = tid;                                   // this thread's sample inside the tile
 
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+  // prefetch of one (tile, chunk) step: raw channel values of sample m into registers
+  float v[TC_KC];
+  auto prefetch = [&](int tile, int chunk) {
+    const int n = tile / tiles_per_n;
+    const int lm = (tile - n * tiles_per_n) * TC_M + m;
+    const int k0 = chunk * TC_KC;
+#pragma unroll
+    for (int r = 0; r < TC_KC; ++r) {
+      v[r] = 0.f;
+      if (k0 + r < Cin && lm < L) {
+        const TcChan& c = ch_s[k0 + r];
+        v[r] = __ldg(c.x + (long long)n * c.nstride + lm);
+      }
+    }
+  };
+
+  int tile = blockIdx.x, chunk = 0;
+  if (tile < total) prefetch(tile, 0);
+  while (tile < total) {
     const int n = tile / tiles_per_n;
     const int l0 = (tile - n * tiles_per_n) * TC_M;
-    for (int k0 = 0; k0 < Cin; k0 += TC_KC) {
-      // ---- stage A: thread = sample m of the tile; channels k0..k0+31 gathered 4 at a time into the
-      //      canonical K-major (no swizzle) layout: [k/8][m/8][(k%8)/4][m%8][k%4]  (hi and lo parts) ----------
-      {
-        const int m = tid;                      // TC_M == TC_NT
-        const int lm = l0 + m;
-        float v[TC_KC];
+    const int k0 = chunk * TC_KC;
+    // the previous MMA batch reads the A (and streamed B) buffers: wait for it before overwriting them
+    if (pending) {
+      if (!tc_wait(bar_addr, parity)) failed = true;
+      parity ^= 1;
+      pending = false;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    // ---- transform + split + store this thread's sample: canonical K-major [k/8][m/8][(k%8)/4][m%8][k%4] ----
+    {
+      const bool inb = (l0 + m) < L;
 #pragma unroll
-        for (int r = 0; r < TC_KC; ++r) {
-          v[r] = 0.f;
-          if (k0 + r < Cin && lm < L) {
-            int cv;
-            const int vi = resolve_view(op, k0 + r, cv);
-            v[r] = __ldg(view_row(op.in[vi], n, cv) + lm);
+      for (int r4 = 0; r4 < TC_KC; r4 += 4) {
+        float t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = r4 + j;
+          t[j] = 0.f;
+          if (k0 + r < Cin && inb) {
+            const TcChan& c = ch_s[k0 + r];
+            float u = fmaf(c.sc, v[r], c.sh);
+            if (c.act == SEIST_ACT_GELU) u = gelu_f(u);
+            t[j] = u;
           }
         }
-#pragma unroll
-        for (int r = 0; r < TC_KC; ++r) {
-          float t = 0.f;
-          if (k0 + r < Cin && lm < L) {
-            int cv;
-            const int vi = resolve_view(op, k0 + r, cv);
-            const SeistView& vw = op.in[vi];
-            float sc, sh;
-            view_coef(op, vw, cv, sc, sh);
-            t = fmaf(sc, v[r], sh);
-            if (vw.act == SEIST_ACT_GELU) t = gelu_f(t);
-          }
-          v[r] = t;
-        }
-#pragma unroll
-        for (int r4 = 0; r4 < TC_KC; r4 += 4) {
-          float4 hi, lo;
-          tc_split(v[r4], hi.x, lo.x);
-          tc_split(v[r4 + 1], hi.y, lo.y);
-          tc_split(v[r4 + 2], hi.z, lo.z);
-          tc_split(v[r4 + 3], hi.w, lo.w);
-          const int off = (r4 >> 3) * 4096 + (m >> 3) * 256 + ((r4 & 7) >> 2) * 128 + (m & 7) * 16;
-          *reinterpret_cast<float4*>(a_hi + off) = hi;
-          *reinterpret_cast<float4*>(a_lo + off) = lo;
-        }
+        float4 hi, lo;
+        tc_split(t[0], hi.x, lo.x);
+        tc_split(t[1], hi.y, lo.y);
+        tc_split(t[2], hi.z, lo.z);
+        tc_split(t[3], hi.w, lo.w);
+        const int off = (r4 >> 3) * 4096 + (m >> 3) * 256 + ((r4 & 7) >> 2) * 128 + (m & 7) * 16;
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        *reinterpret_cast<float4*>(a_lo + off) = lo;
       }
-      // ---- stage B: weights chunk -> canonical K-major (no swizzle), hi and lo parts ---------------------
-      for (int idx = tid; idx < N_pad * TC_KC; idx += TC_NT) {
-        const int k = idx % TC_KC, nn = idx / TC_KC;
-        float w = 0.f;
-        if (nn < Cout && k0 + k < Cin) w = op.W[(size_t)nn * Cin + k0 + k];
-        float hi, lo;
-        tc_split(w, hi, lo);
-        const int off = (k >> 3) * (N_pad * 32) + (nn >> 3) * 256 + ((k & 7) >> 2) * 128 + (nn & 7) * 16 + (k & 3) * 4;
-        *reinterpret_cast<float*>(b_hi + off) = hi;
-        *reinterpret_cast<float*>(b_lo + off) = lo;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (tensor core)
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi_u = tc_smem_u32(a_hi), a_lo_u = tc_smem_u32(a_lo);
-        const uint32_t b_hi_u = tc_smem_u32(b_hi), b_lo_u = tc_smem_u32(b_lo);
+    }
+    if (!b_resident) stage_b(chunk, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (tensor core)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi_u = tc_smem_u32(a_hi), a_lo_u = tc_smem_u32(a_lo);
+      const int slot = b_resident ? chunk : 0;
+      const uint32_t b_hi_u = tc_smem_u32(b_hi) + slot * b_chunk_bytes, b_lo_u = tc_smem_u32(b_lo) + slot * b_chunk_bytes;
 #pragma unroll
-        for (int kb = 0; kb < TC_KC / 8; ++kb) {
+      for (int kb = 0; kb < TC_KC / 8; ++kb) {
+        if (k0 + kb * 8 < Cin) {
           const uint64_t ah = tc_desc(a_hi_u + kb * 4096, 128, 256, 0);
           const uint64_t al = tc_desc(a_lo_u + kb * 4096, 128, 256, 0);
           const uint64_t bh = tc_desc(b_hi_u + kb * N_pad * 32, 128, 256, 0);
           const uint64_t bl = tc_desc(b_lo_u + kb * N_pad * 32, 128, 256, 0);
-          tc_mma_tf32(tmem_base, ah, bh, idesc, (k0 > 0 || kb > 0) ? 1u : 0u);
+          tc_mma_tf32(tmem_base, ah, bh, idesc, (chunk > 0 || kb > 0) ? 1u : 0u);
           tc_mma_tf32(tmem_base, al, bh, idesc, 1u);
           tc_mma_tf32(tmem_base, ah, bl, idesc, 1u);
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr)
-                     : "memory");
       }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+    }
+    pending = true;
+    // ---- next step: issue its global loads now so they fly while the tensor core works -------------------
+    const bool last_chunk = (chunk + 1 == nchunks);
+    const int next_tile = last_chunk ? tile + gridDim.x : tile;
+    const int next_chunk = last_chunk ? 0 : chunk + 1;
+    if (next_tile < total) prefetch(next_tile, next_chunk);
+
+    if (last_chunk) {
       if (!tc_wait(bar_addr, parity)) failed = true;
       parity ^= 1;
+      pending = false;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-
-    // ---- epilogue: lane = sample (TMEM lane 32*warp + lane), 16 output channels per tcgen05.ld -------------
-    const int l = l0 + 32 * warp + lane;
-    const bool ok = l < L;
-    const float pf = path_factor(op, seed, n), af = alpha_factor(op, seed, n);
-    for (int c0 = 0; c0 < Cout; c0 += 16) {
-      uint32_t rr[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]),
-            "=r"(rr[8]), "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // ---- epilogue: lane = sample (TMEM lane 32*warp + lane), 16 output channels per tcgen05.ld ----------
+      const int l = l0 + m;
+      const bool ok = l < L;
+      const float pf = path_factor(op, seed, n), af = alpha_factor(op, seed, n);
+      for (int c0 = 0; c0 < Cout; c0 += 16) {
+        uint32_t rr[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]),
+              "=r"(rr[8]), "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float s1[16], s2[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int co = c0 + c;
-        if (co >= Cout) break;
-        float s1 = 0.f, s2 = 0.f;
-        if (ok) {
-          float v = (__uint_as_float(rr[c]) + ep_s[co]) * pf * elem_factor(op, seed, n, co, l);
-          if (op.res_a.C > 0) v += fmaf(ep_s[Cout + co], view_row(op.res_a, n, co)[l], ep_s[2 * Cout + co]);
-          v *= af;
-          if (op.res_b.C > 0) v += fmaf(ep_s[3 * Cout + co], view_row(op.res_b, n, co)[l], ep_s[4 * Cout + co]);
-          if (op.out_act == SEIST_OUT_SIGMOID) v = sigmoid_f(v);
-          op.out.x[((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l] = v;
-          s1 = v;
-          s2 = v * v;
+        for (int c = 0; c < 16; ++c) {
+          const int co = c0 + c;
+          float val = 0.f;
+          if (ok && co < Cout) {
+            val = (__uint_as_float(rr[c]) + ep_s[co]) * pf * elem_factor(op, seed, n, co, l);
+            if (op.res_a.C > 0) val += fmaf(ep_s[Cout + co], view_row(op.res_a, n, co)[l], ep_s[2 * Cout + co]);
+            val *= af;
+            if (op.res_b.C > 0) val += fmaf(ep_s[3 * Cout + co], view_row(op.res_b, n, co)[l], ep_s[4 * Cout + co]);
+            if (op.out_act == SEIST_OUT_SIGMOID) val = sigmoid_f(val);
+            op.out.x[((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l] = val;
+          }
+          s1[c] = val;
+          s2[c] = val * val;
         }
         if (stats) {
-          s1 = warp_sum(s1);
-          s2 = warp_sum(s2);
-          if (lane == 0) {
-            atomicAdd(&red_s[2 * co], s1);
-            atomicAdd(&red_s[2 * co + 1], s2);
+          const float t1 = tc_reduce16(s1, lane), t2 = tc_reduce16(s2, lane);
+          const int co = c0 + tc_reduce16_index(lane);
+          if ((lane & 1) == 0 && co < Cout) {          // single writer per (warp, channel): deterministic
+            red_s[warp * 2 * Cout + 2 * co] += t1;
+            red_s[warp * 2 * Cout + 2 * co + 1] += t2;
           }
         }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();       // all TMEM reads of this tile are done before the next tile's MMAs overwrite it
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();       // all TMEM reads of this tile are done before the next tile's MMAs overwrite it
+    tile = next_tile;
+    chunk = next_chunk;
   }
 
   if (stats) {
     __syncthreads();
     const SeistBN& e = op.bn_table[op.out.bn];
-    for (int i = tid; i < 2 * Cout; i += TC_NT)
-      atomicAdd(&e.stat[(i & 1) * e.C + op.out.bn_c0 + (i >> 1)], (double)red_s[i]);
+    for (int i = tid; i < 2 * Cout; i += TC_NT) {
+      const float s = (red_s[i] + red_s[2 * Cout + i]) + (red_s[4 * Cout + i] + red_s[6 * Cout + i]);
+      atomicAdd(&e.stat[(i & 1) * e.C + op.out.bn_c0 + (i >> 1)], (double)s);
+    }
   }
   __syncthreads();
   if (warp == 0) {
@@ -275,8 +351,11 @@ int launch_pw_tc_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int N_pad = (op.Cout + 15) & ~15;
   int cols = 32;
   while (cols < N_pad) cols <<= 1;
-  const size_t smem = 2 * (size_t)TC_A_BYTES + 2 * (size_t)(TC_KC / 8) * N_pad * 32 + sizeof(float) * (7 * (size_t)op.Cout + 2) +
-                      16 + 1024;
+  const int nchunks = (op.Cin + TC_KC - 1) / TC_KC;
+  const size_t b_chunk = (size_t)(TC_KC / 8) * N_pad * 32;
+  const int b_resident = (2 * nchunks * b_chunk <= 64 * 1024) ? 1 : 0;
+  const size_t smem = 2 * (size_t)TC_A_BYTES + 2 * (b_resident ? nchunks : 1) * b_chunk + sizeof(float) * (13 * (size_t)op.Cout + 2) +
+                      32 + sizeof(TcChan) * (size_t)op.Cin + 1024;
   static size_t max_set = 0;
   if (smem > max_set) {
     cudaError_t e = cudaFuncSetAttribute(pw_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem < 49152 ? 49152 : smem));
@@ -286,7 +365,7 @@ int launch_pw_tc_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
   const long tiles = (long)op.N * ((op.L_out + TC_M - 1) / TC_M);
   long g = 4L * sm_count;
   if (g > tiles) g = tiles;
-  pw_tc_fwd_kernel<<<(unsigned)(g < 1 ? 1 : g), TC_NT, smem, s>>>(op, N_pad, cols);
+  pw_tc_fwd_kernel<<<(unsigned)(g < 1 ? 1 : g), TC_NT, smem, s>>>(op, N_pad, cols, b_resident);
   note_launch();
   return check_launch("pw_tc_fwd");
 }
