@@ -52,10 +52,10 @@ int launch_convk_bwd_data(const SeistOp& op, cudaStream_t s);
 int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s);
 int launch_stem_compose(const SeistOp& op, bool fwd, cudaStream_t s);
 
-// tensor-core (tcgen05) path for the 1x1 forward: on unless SEIST_TC=0
+// tensor-core (tcgen05) path for the 1x1 forward: opt-in with SEIST_TC=1 (validated, not yet faster than SIMT)
 static int use_tc() {
   static int v = -1;
-  if (v < 0) { const char* e = std::getenv("SEIST_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = std::getenv("SEIST_TC"); v = (e && e[0] == '1') ? 1 : 0; }
   return v;
 }
 

@@ -79,7 +79,28 @@ __device__ __forceinline__ void cta_reduce_atomic(float (&part)[NV], float* red_
 // forward: out[co] = alpha * [ drop( sum_ci W[co][ci] f(in[ci]) + b ) + res_a ] + res_b
 // grid (ceil(N*L/4 / (128*G)), ceil(Cout/COUT_T))
 // ================================================================================================
-template <int COUT_T>
+__device__ __noinline__ float4 pw_gelu4(float4 v) {
+  v.x = gelu_f(v.x);
+  v.y = gelu_f(v.y);
+  v.z = gelu_f(v.z);
+  v.w = gelu_f(v.w);
+  return v;
+}
+__device__ __noinline__ float4 pw_gelu_grad4(float4 u) {
+  u.x = gelu_grad_f(u.x);
+  u.y = gelu_grad_f(u.y);
+  u.z = gelu_grad_f(u.z);
+  u.w = gelu_grad_f(u.w);
+  return u;
+}
+__device__ __noinline__ float4 pw_keep4(float p, uint64_t seed, uint32_t stream, uint64_t idx) {
+  return make_float4(keep_scale(p, seed, stream, idx), keep_scale(p, seed, stream, idx + 1),
+                     keep_scale(p, seed, stream, idx + 2), keep_scale(p, seed, stream, idx + 3));
+}
+
+// compile-time specialisation keeps the bodies small (instruction cache) and the inner loops free of
+// runtime feature tests: F_ELEM element dropout, F_RES residual views, F_GELU some view applies GELU
+template <int COUT_T, bool F_ELEM, bool F_RES, bool F_GELU>
 __global__ void __launch_bounds__(PW_NT) pw_fwd_kernel(const __grid_constant__ SeistOp op, const int G) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cin = op.Cin, Cin8 = (Cin + 7) & ~7;
@@ -146,7 +167,8 @@ __global__ void __launch_bounds__(PW_NT) pw_fwd_kernel(const __grid_constant__ S
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const PwChan& c = ch_s[ci0 + j];
-        const float4 u = apply_view(v[j], c.sc, c.sh, c.act);
+        float4 u = apply_view(v[j], c.sc, c.sh, 0);
+        if (F_GELU && c.act == SEIST_ACT_GELU) u = pw_gelu4(u);
         const float* wr = w_s + (ci0 + j) * COUT_T;
 #pragma unroll
         for (int co = 0; co < COUT_T; ++co) {
@@ -170,14 +192,14 @@ __global__ void __launch_bounds__(PW_NT) pw_fwd_kernel(const __grid_constant__ S
       r.y = (r.y + b) * pf;
       r.z = (r.z + b) * pf;
       r.w = (r.w + b) * pf;
-      if (op.p_elem > 0.f) {
-        const uint64_t idx = ((uint64_t)n * op.Cout + co) * (uint64_t)L + l;
-        r.x *= keep_scale(op.p_elem, seed, op.seed_elem, idx);
-        r.y *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 1);
-        r.z *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 2);
-        r.w *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 3);
+      if (F_ELEM) {
+        const float4 kp = pw_keep4(op.p_elem, seed, op.seed_elem, ((uint64_t)n * op.Cout + co) * (uint64_t)L + l);
+        r.x *= kp.x;
+        r.y *= kp.y;
+        r.z *= kp.z;
+        r.w *= kp.w;
       }
-      if (op.res_a.C > 0) {
+      if (F_RES && op.res_a.C > 0) {
         const float4 a = ldg4(op.res_a.x + ((size_t)n * op.res_a.Ct + op.res_a.c0 + co) * (size_t)L + l);
         const float sc = ep_s[COUT_T + col], sh = ep_s[2 * COUT_T + col];
         r.x += fmaf(sc, a.x, sh);
@@ -189,7 +211,7 @@ __global__ void __launch_bounds__(PW_NT) pw_fwd_kernel(const __grid_constant__ S
       r.y *= af;
       r.z *= af;
       r.w *= af;
-      if (op.res_b.C > 0) {
+      if (F_RES && op.res_b.C > 0) {
         const float4 a = ldg4(op.res_b.x + ((size_t)n * op.res_b.Ct + op.res_b.c0 + co) * (size_t)L + l);
         const float sc = ep_s[3 * COUT_T + col], sh = ep_s[4 * COUT_T + col];
         r.x += fmaf(sc, a.x, sh);
@@ -227,7 +249,7 @@ struct PwOut {   // per output channel of the forward op, resolved once per CTA
   float A, Bx, Cc;
 };
 
-template <int CI_T>
+template <int CI_T, bool F_ELEM, bool F_GELU>
 __global__ void __launch_bounds__(PW_NT) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cout = op.Cout, Cout4 = (Cout + 3) & ~3, Cin = op.Cin;
@@ -309,12 +331,12 @@ __global__ void __launch_bounds__(PW_NT) pw_bwd_data_kernel(const __grid_constan
         gv.y *= pf;
         gv.z *= pf;
         gv.w *= pf;
-        if (op.p_elem > 0.f) {
-          const uint64_t idx = ((uint64_t)n * Cout + min(co, Cout - 1)) * (uint64_t)L + l;
-          gv.x *= keep_scale(op.p_elem, seed, op.seed_elem, idx);
-          gv.y *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 1);
-          gv.z *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 2);
-          gv.w *= keep_scale(op.p_elem, seed, op.seed_elem, idx + 3);
+        if (F_ELEM) {
+          const float4 kp = pw_keep4(op.p_elem, seed, op.seed_elem, ((uint64_t)n * Cout + min(co, Cout - 1)) * (uint64_t)L + l);
+          gv.x *= kp.x;
+          gv.y *= kp.y;
+          gv.z *= kp.z;
+          gv.w *= kp.w;
         }
         const float* wr = w_s + co * CI_T;   // zero rows for co >= Cout
 #pragma unroll
@@ -335,12 +357,14 @@ __global__ void __launch_bounds__(PW_NT) pw_bwd_data_kernel(const __grid_constan
       float4 gg = acc[col];
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       const long long off = (long long)n * c.nstride + l;
-      if (c.act == SEIST_ACT_GELU || c.bn >= 0) x = ldg4(c.x + off);
-      if (c.act == SEIST_ACT_GELU) {
-        gg.x *= gelu_grad_f(fmaf(c.sc, x.x, c.sh));
-        gg.y *= gelu_grad_f(fmaf(c.sc, x.y, c.sh));
-        gg.z *= gelu_grad_f(fmaf(c.sc, x.z, c.sh));
-        gg.w *= gelu_grad_f(fmaf(c.sc, x.w, c.sh));
+      if ((F_GELU && c.act == SEIST_ACT_GELU) || c.bn >= 0) x = ldg4(c.x + off);
+      if (F_GELU && c.act == SEIST_ACT_GELU) {
+        const float4 d = pw_gelu_grad4(make_float4(fmaf(c.sc, x.x, c.sh), fmaf(c.sc, x.y, c.sh), fmaf(c.sc, x.z, c.sh),
+                                                   fmaf(c.sc, x.w, c.sh)));
+        gg.x *= d.x;
+        gg.y *= d.y;
+        gg.z *= d.z;
+        gg.w *= d.w;
       }
       if (c.bn >= 0) {
         st[2 * col] += (gg.x + gg.y) + (gg.z + gg.w);
@@ -477,6 +501,33 @@ static int pw_set_smem(K kernel, size_t bytes) {
   return 0;
 }
 
+static bool any_gelu(const SeistOp& op) {
+  for (int i = 0; i < op.n_in; ++i)
+    if (op.in[i].act == SEIST_ACT_GELU) return true;
+  return false;
+}
+
+template <int COT, bool E, bool R, bool Gf>
+static int pw_fwd_go(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
+  int rc = pw_set_smem(pw_fwd_kernel<COT, E, R, Gf>, smem);
+  if (!rc) pw_fwd_kernel<COT, E, R, Gf><<<grid, PW_NT, smem, s>>>(op, G);
+  return rc;
+}
+template <int COT>
+static int pw_fwd_sel(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
+  const int sel = (op.p_elem > 0.f ? 4 : 0) | ((op.res_a.C > 0 || op.res_b.C > 0) ? 2 : 0) | (any_gelu(op) ? 1 : 0);
+  switch (sel) {
+    case 0: return pw_fwd_go<COT, false, false, false>(op, s, grid, smem, G);
+    case 1: return pw_fwd_go<COT, false, false, true>(op, s, grid, smem, G);
+    case 2: return pw_fwd_go<COT, false, true, false>(op, s, grid, smem, G);
+    case 3: return pw_fwd_go<COT, false, true, true>(op, s, grid, smem, G);
+    case 4: return pw_fwd_go<COT, true, false, false>(op, s, grid, smem, G);
+    case 5: return pw_fwd_go<COT, true, false, true>(op, s, grid, smem, G);
+    case 6: return pw_fwd_go<COT, true, true, false>(op, s, grid, smem, G);
+    default: return pw_fwd_go<COT, true, true, true>(op, s, grid, smem, G);
+  }
+}
+
 int launch_pw_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int cot = op.Cout > 8 ? 16 : 8;
   const int Cin8 = (op.Cin + 7) & ~7;
@@ -485,17 +536,27 @@ int launch_pw_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int ty = (op.Cout + cot - 1) / cot;
   const int G = pick_G(nq, ty, sm_count);
   dim3 grid((unsigned)((nq + (long long)PW_NT * G - 1) / ((long long)PW_NT * G)), ty);
-  int rc = 0;
-  if (cot == 16) {
-    rc = pw_set_smem(pw_fwd_kernel<16>, smem);
-    if (!rc) pw_fwd_kernel<16><<<grid, PW_NT, smem, s>>>(op, G);
-  } else {
-    rc = pw_set_smem(pw_fwd_kernel<8>, smem);
-    if (!rc) pw_fwd_kernel<8><<<grid, PW_NT, smem, s>>>(op, G);
-  }
+  const int rc = cot == 16 ? pw_fwd_sel<16>(op, s, grid, smem, G) : pw_fwd_sel<8>(op, s, grid, smem, G);
   if (rc) return rc;
   note_launch();
   return check_launch("pw_fwd");
+}
+
+template <int CIT, bool E, bool Gf>
+static int pw_bwdd_go(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
+  int rc = pw_set_smem(pw_bwd_data_kernel<CIT, E, Gf>, smem);
+  if (!rc) pw_bwd_data_kernel<CIT, E, Gf><<<grid, PW_NT, smem, s>>>(op, G);
+  return rc;
+}
+template <int CIT>
+static int pw_bwdd_sel(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
+  const int sel = (op.p_elem > 0.f ? 2 : 0) | (any_gelu(op) ? 1 : 0);
+  switch (sel) {
+    case 0: return pw_bwdd_go<CIT, false, false>(op, s, grid, smem, G);
+    case 1: return pw_bwdd_go<CIT, false, true>(op, s, grid, smem, G);
+    case 2: return pw_bwdd_go<CIT, true, false>(op, s, grid, smem, G);
+    default: return pw_bwdd_go<CIT, true, true>(op, s, grid, smem, G);
+  }
 }
 
 int launch_pw_bwd_data(const SeistOp& op, cudaStream_t s, int sm_count) {
@@ -506,14 +567,7 @@ int launch_pw_bwd_data(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int ty = (op.Cin + cit - 1) / cit;
   const int G = pick_G(nq, ty, sm_count);
   dim3 grid((unsigned)((nq + (long long)PW_NT * G - 1) / ((long long)PW_NT * G)), ty);
-  int rc = 0;
-  if (cit == 16) {
-    rc = pw_set_smem(pw_bwd_data_kernel<16>, smem);
-    if (!rc) pw_bwd_data_kernel<16><<<grid, PW_NT, smem, s>>>(op, G);
-  } else {
-    rc = pw_set_smem(pw_bwd_data_kernel<8>, smem);
-    if (!rc) pw_bwd_data_kernel<8><<<grid, PW_NT, smem, s>>>(op, G);
-  }
+  const int rc = cit == 16 ? pw_bwdd_sel<16>(op, s, grid, smem, G) : pw_bwdd_sel<8>(op, s, grid, smem, G);
   if (rc) return rc;
   note_launch();
   return check_launch("pw_bwd_data");

@@ -96,6 +96,10 @@ __device__ __forceinline__ int tc_reduce16_index(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+__device__ __noinline__ float tc_gelu(float x) { return gelu_f(x); }     // shared body: keeps the kernel I-cache sized
+
+// F_ELEM: element dropout in the epilogue; F_RES: residual views; F_GELU: some input view applies GELU
+template <bool F_ELEM, bool F_RES, bool F_GELU>
 __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant__ SeistOp op, const int N_pad,
                                                           const int tmem_cols, const int b_resident) {
   extern __shared__ __align__(16) unsigned char tc_raw[];
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant_
           if (k0 + r < Cin && inb) {
             const TcChan& c = ch_s[k0 + r];
             float u = fmaf(c.sc, v[r], c.sh);
-            if (c.act == SEIST_ACT_GELU) u = gelu_f(u);
+            if (F_GELU && c.act == SEIST_ACT_GELU) u = tc_gelu(u);
             t[j] = u;
           }
         }
@@ -281,6 +285,10 @@ __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant_
       const int l = l0 + m;
       const bool ok = l < L;
       const float pf = path_factor(op, seed, n), af = alpha_factor(op, seed, n);
+      float* optr = op.out.x + ((size_t)n * op.out.Ct + op.out.c0) * (size_t)L + l;
+      const float* ra = F_RES && op.res_a.C > 0 ? op.res_a.x + ((size_t)n * op.res_a.Ct + op.res_a.c0) * (size_t)L + l : nullptr;
+      const float* rb = F_RES && op.res_b.C > 0 ? op.res_b.x + ((size_t)n * op.res_b.Ct + op.res_b.c0) * (size_t)L + l : nullptr;
+#pragma unroll 1
       for (int c0 = 0; c0 < Cout; c0 += 16) {
         uint32_t rr[16];
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0;
@@ -297,12 +305,17 @@ __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant_
           const int co = c0 + c;
           float val = 0.f;
           if (ok && co < Cout) {
-            val = (__uint_as_float(rr[c]) + ep_s[co]) * pf * elem_factor(op, seed, n, co, l);
-            if (op.res_a.C > 0) val += fmaf(ep_s[Cout + co], view_row(op.res_a, n, co)[l], ep_s[2 * Cout + co]);
-            val *= af;
-            if (op.res_b.C > 0) val += fmaf(ep_s[3 * Cout + co], view_row(op.res_b, n, co)[l], ep_s[4 * Cout + co]);
+            val = (__uint_as_float(rr[c]) + ep_s[co]) * pf;
+            if (F_ELEM) val *= elem_factor(op, seed, n, co, l);
+            if (F_RES) {
+              if (ra) val += fmaf(ep_s[Cout + co], ra[(size_t)co * L], ep_s[2 * Cout + co]);
+              val *= af;
+              if (rb) val += fmaf(ep_s[3 * Cout + co], rb[(size_t)co * L], ep_s[4 * Cout + co]);
+            } else {
+              val *= af;
+            }
             if (op.out_act == SEIST_OUT_SIGMOID) val = sigmoid_f(val);
-            op.out.x[((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l] = val;
+            optr[(size_t)co * L] = val;
           }
           s1[c] = val;
           s2[c] = val * val;
@@ -356,16 +369,38 @@ int launch_pw_tc_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int b_resident = (2 * nchunks * b_chunk <= 64 * 1024) ? 1 : 0;
   const size_t smem = 2 * (size_t)TC_A_BYTES + 2 * (b_resident ? nchunks : 1) * b_chunk + sizeof(float) * (13 * (size_t)op.Cout + 2) +
                       32 + sizeof(TcChan) * (size_t)op.Cin + 1024;
-  static size_t max_set = 0;
-  if (smem > max_set) {
-    cudaError_t e = cudaFuncSetAttribute(pw_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem < 49152 ? 49152 : smem));
-    if (e != cudaSuccess) return (int)e;
-    max_set = smem;
-  }
   const long tiles = (long)op.N * ((op.L_out + TC_M - 1) / TC_M);
   long g = 4L * sm_count;
   if (g > tiles) g = tiles;
-  pw_tc_fwd_kernel<<<(unsigned)(g < 1 ? 1 : g), TC_NT, smem, s>>>(op, N_pad, cols, b_resident);
+  const unsigned grid = (unsigned)(g < 1 ? 1 : g);
+  const bool f_elem = op.p_elem > 0.f, f_res = op.res_a.C > 0 || op.res_b.C > 0;
+  bool f_gelu = false;
+  for (int i = 0; i < op.n_in; ++i) f_gelu = f_gelu || op.in[i].act == SEIST_ACT_GELU;
+  int rc = 0;
+#define TC_LAUNCH(E, R, G)                                                                                           \
+  {                                                                                                                   \
+    static size_t max_set = 0;                                                                                        \
+    if (smem > max_set) {                                                                                             \
+      cudaError_t e = cudaFuncSetAttribute(pw_tc_fwd_kernel<E, R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           (int)(smem < 49152 ? 49152 : smem));                                       \
+      if (e != cudaSuccess) rc = (int)e;                                                                              \
+      max_set = smem;                                                                                                 \
+    }                                                                                                                 \
+    if (!rc) pw_tc_fwd_kernel<E, R, G><<<grid, TC_NT, smem, s>>>(op, N_pad, cols, b_resident);                        \
+  }
+  const int sel = (f_elem ? 4 : 0) | (f_res ? 2 : 0) | (f_gelu ? 1 : 0);
+  switch (sel) {
+    case 0: TC_LAUNCH(false, false, false) break;
+    case 1: TC_LAUNCH(false, false, true) break;
+    case 2: TC_LAUNCH(false, true, false) break;
+    case 3: TC_LAUNCH(false, true, true) break;
+    case 4: TC_LAUNCH(true, false, false) break;
+    case 5: TC_LAUNCH(true, false, true) break;
+    case 6: TC_LAUNCH(true, true, false) break;
+    default: TC_LAUNCH(true, true, true) break;
+  }
+#undef TC_LAUNCH
+  if (rc) return rc;
   note_launch();
   return check_launch("pw_tc_fwd");
 }
