@@ -594,11 +594,11 @@ int launch_res_bwd4(const SeistOp& op, cudaStream_t s, int sm_count) {
 // are folded through shared memory once at the end; one float atomic per dW element per CTA.
 // ================================================================================================
 constexpr int BW_NT = 256;
-constexpr int BW_PC = 128;            // output samples per chunk
-constexpr int BW_PITCH = BW_PC + 4;   // gacc row pitch (floats), keeps 16-byte alignment
 
-template <int CO_B, int R_B, bool K1>
+// BW_PC = output samples per chunk (128, or 512 for narrow tiles where the per-chunk barriers/latency dominate)
+template <int CO_B, int R_B, bool K1, int BW_PC>
 __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ SeistOp op, const int nci_max) {
+  constexpr int BW_PITCH = BW_PC + 4;   // gacc row pitch (floats), keeps 16-byte alignment
   extern __shared__ __align__(16) unsigned char sm_raw[];
   constexpr int TGM = CO_B / 4, TGN = R_B / 8, TG = TGM * TGN, PG = BW_NT / TG;
   static_assert(TG <= BW_NT && BW_NT % TG == 0, "bad tile");
@@ -822,8 +822,9 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
   }
 }
 
-template <int CO_B, int R_B, bool K1>
-static int launch_bww(const SeistOp& op, cudaStream_t s, int sm_count) {
+template <int CO_B, int R_B, bool K1, int BW_PC>
+static int launch_bww_pc(const SeistOp& op, cudaStream_t s, int sm_count) {
+  constexpr int BW_PITCH = BW_PC + 4;
   const int k = op.k, S = op.stride;
   int nci_max = (R_B + k - 1) / k + 1;
   if (nci_max > op.Cin) nci_max = op.Cin;
@@ -839,11 +840,20 @@ static int launch_bww(const SeistOp& op, cudaStream_t s, int sm_count) {
   long gx = (2L * sm_count + gy * gz - 1) / (gy * gz);
   if (gx > tiles) gx = tiles;
   if (gx < 1) gx = 1;
-  int rc = pw_set_smem(bww_kernel<CO_B, R_B, K1>, smem);
+  int rc = pw_set_smem(bww_kernel<CO_B, R_B, K1, BW_PC>, smem);
   if (rc) return rc;
-  bww_kernel<CO_B, R_B, K1><<<dim3((unsigned)gx, gy, gz), BW_NT, smem, s>>>(op, nci_max);
+  bww_kernel<CO_B, R_B, K1, BW_PC><<<dim3((unsigned)gx, gy, gz), BW_NT, smem, s>>>(op, nci_max);
   note_launch();
   return check_launch("bww");
+}
+
+template <int CO_B, int R_B, bool K1>
+static int launch_bww(const SeistOp& op, cudaStream_t s, int sm_count) {
+  int nci = (R_B + op.k - 1) / op.k + 1;
+  if (nci > op.Cin) nci = op.Cin;
+  // narrow tiles (few rows to stage) and long rows: 512-sample chunks
+  if (CO_B <= 16 && nci <= 16 && op.L_out >= 2048 && op.stride == 1) return launch_bww_pc<CO_B, R_B, K1, 512>(op, s, sm_count);
+  return launch_bww_pc<CO_B, R_B, K1, 128>(op, s, sm_count);
 }
 
 template <bool K1>
