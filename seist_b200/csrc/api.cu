@@ -52,11 +52,21 @@ int launch_convk_bwd_data(const SeistOp& op, cudaStream_t s);
 int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s);
 int launch_stem_compose(const SeistOp& op, bool fwd, cudaStream_t s);
 
-// tensor-core (tcgen05) path for the 1x1 forward: opt-in with SEIST_TC=1 (validated, not yet faster than SIMT)
-static int use_tc() {
+// tensor-core (tcgen05) path for the 1x1 forward.  SEIST_TC=0: never; SEIST_TC=1: every eligible op; default:
+// where it measured faster than the streaming SIMT kernel on B200 (profiles/): GELU-prologue inputs (the
+// activation is evaluated once per element instead of once per 16 output channels) and wide contractions.
+static int tc_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = std::getenv("SEIST_TC"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = std::getenv("SEIST_TC"); v = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)); }
   return v;
+}
+static bool use_tc(const SeistOp& op) {
+  const int mode = tc_mode();
+  if (mode == 0 || !pw_tc_eligible(op)) return false;
+  if (mode == 1) return true;
+  bool gelu = false;
+  for (int i = 0; i < op.n_in; ++i) gelu = gelu || op.in[i].act == SEIST_ACT_GELU;
+  return (gelu && op.Cin >= 32 && op.Cout >= 16) || (op.Cin >= 64 && op.Cout >= 32);
 }
 
 static int sm_count() {
@@ -81,7 +91,7 @@ static int validate_conv(const SeistOp& op) {
 
 static int run_one(const SeistOp& op, cudaStream_t s) {
   switch (op.kind) {
-    case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (use_tc() && pw_tc_eligible(op)) return launch_pw_tc_fwd(op, s, sm_count()); if (pw_eligible(op)) return launch_pw_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
+    case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (use_tc(op)) return launch_pw_tc_fwd(op, s, sm_count()); if (pw_eligible(op)) return launch_pw_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
     case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); if (v) return v; if (pw_eligible(op)) return launch_pw_bwd_data(op, s, sm_count()); return (convk_eligible(op) && op.stride == 1) ? launch_convk_bwd_data(op, s) : launch_conv_bwd_data(op, s); }
     case SEIST_OP_CONV_BWD_W: { int v = validate_conv(op); if (v) return v; return bww_eligible(op) ? launch_bww_any(op, s, sm_count()) : launch_conv_bwd_w(op, s, sm_count()); }
     case SEIST_OP_RES_BWD: return (op.L_out & 3) ? launch_res_bwd(op, s) : launch_res_bwd4(op, s, sm_count());
