@@ -96,7 +96,12 @@ __global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant_
   const int WP = 8 / WC, CO_B = 8 * WC, TLo = 128 * WP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wc = warp % WC, wp = warp / WC;
-  const int n = blockIdx.y, l0 = blockIdx.x * TLo, co_base = blockIdx.z * CO_B;
+  const int gs_in = op.Cin / op.groups, gs_out = op.Cout / op.groups;
+  const int tpg = (gs_out + CO_B - 1) / CO_B;          // output-channel tiles per group
+  const int grp = blockIdx.z / tpg;
+  const int n = blockIdx.y, l0 = blockIdx.x * TLo, co_base = grp * gs_out + (blockIdx.z - grp * tpg) * CO_B;
+  const int co_end = (grp + 1) * gs_out;               // channels of this group only
+  const int ci_grp = grp * gs_in;
   const int width = TLo * S + K - S;
   const int pitch = ((width + 3) & ~3) + 4;
   float* in_s = ck_smem;                               // [CIC][pitch]
@@ -113,20 +118,20 @@ __global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant_
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
 
-  for (int ci0 = 0; ci0 < op.Cin; ci0 += CK_CIC) {
-    const int cic = min(CK_CIC, op.Cin - ci0);
+  for (int ci0 = 0; ci0 < gs_in; ci0 += CK_CIC) {
+    const int cic = min(CK_CIC, gs_in - ci0);
     if (op.up_src_L > 0) {
-      stage_upsampled_rows(op, n, ci0, cic, in_s, pitch, width, p_base, src_s, width + 4, Lsrc, ratio);
+      stage_upsampled_rows(op, n, ci_grp + ci0, cic, in_s, pitch, width, p_base, src_s, width + 4, Lsrc, ratio);
       for (int r = cic + warp; r < CK_CIC; r += CK_NT / 32)
         for (int pos = lane; pos < width; pos += 32) in_s[r * pitch + pos] = 0.f;
     } else {
-      ck_stage_input(op, n, ci0, cic, in_s, pitch, width, p_base, Lsrc, ratio);
+      ck_stage_input(op, n, ci_grp + ci0, cic, in_s, pitch, width, p_base, Lsrc, ratio);
     }
     for (int idx = tid; idx < CK_CIC * K * CO_B; idx += CK_NT) {
       const int col = idx % CO_B, rest = idx / CO_B;
       const int t = rest % K, r = rest / K;
       const int co = co_base + col;
-      w_s[idx] = (r < cic && co < op.Cout) ? op.W[((size_t)co * op.Cin + ci0 + r) * K + t] : 0.f;
+      w_s[idx] = (r < cic && co < co_end) ? op.W[((size_t)co * gs_in + ci0 + r) * K + t] : 0.f;
     }
     __syncthreads();
     const float* ib = in_s + (wp * 128 + 4 * lane) * S;
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant_
   for (int c = 0; c < 8; ++c) {
     const int co = co_base + wc * 8 + c;
     float s1 = 0.f, s2 = 0.f;
-    if (co < op.Cout) {
+    if (co < co_end) {
       const float b = op.bias ? op.bias[co] : 0.f;
       float asc = 1.f, ash = 0.f, bsc = 1.f, bsh = 0.f;
       const float *ra = nullptr, *rb = nullptr;
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant_
       float s = 0.f;
       for (int p = 0; p < WP; ++p) s += red_s[(p * WC + w0) * 16 + i];
       const int co = co_base + w0 * 8 + (i >> 1);
-      if (co < op.Cout) {
+      if (co < co_end) {
         const SeistBN& e = op.bn_table[op.out.bn];
         atomicAdd(&e.stat[(i & 1) * e.C + op.out.bn_c0 + co], (double)s);
       }
@@ -215,7 +220,12 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
   const int WP = 8 / WC, CI_B = 8 * WC, TLo = 128 * WP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wc = warp % WC, wp = warp / WC;
-  const int n = blockIdx.y, p0 = blockIdx.x * TLo, ci_base = blockIdx.z * CI_B;
+  const int gs_in = op.Cin / op.groups, gs_out = op.Cout / op.groups;
+  const int tpg = (gs_in + CI_B - 1) / CI_B;
+  const int grp = blockIdx.z / tpg;
+  const int n = blockIdx.y, p0 = blockIdx.x * TLo, ci_base = grp * gs_in + (blockIdx.z - grp * tpg) * CI_B;
+  const int ci_end = (grp + 1) * gs_in;
+  const int co_grp = grp * gs_out;
   const int width = TLo + K - 1;
   const int pitch = ((width + 3) & ~3) + 4;
   float* z_s = ck_smem;                                // [CIC][pitch]
@@ -231,15 +241,15 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
 
-  for (int co0 = 0; co0 < op.Cout; co0 += CK_CIC) {
-    const int coc = min(CK_CIC, op.Cout - co0);
+  for (int co0 = 0; co0 < gs_out; co0 += CK_CIC) {
+    const int coc = min(CK_CIC, gs_out - co0);
     for (int r = warp; r < CK_CIC; r += CK_NT / 32) {
       float* dst = z_s + r * pitch;
       if (r >= coc) {
         for (int pos = lane; pos < width; pos += 32) dst[pos] = 0.f;
         continue;
       }
-      const int co = co0 + r;
+      const int co = co_grp + co0 + r;
       const OutGradCoef kc = out_grad_coef(op, co);
       for (int pos0 = lane; pos0 < width; pos0 += 32 * 4) {
         float v[4];
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
       const int col = idx % CI_B, rest = idx / CI_B;
       const int tf = rest % K, r = rest / K;
       const int ci = ci_base + col;
-      w_s[idx] = (r < coc && ci < op.Cin) ? op.W[((size_t)(co0 + r) * op.Cin + ci) * K + (K - 1 - tf)] : 0.f;
+      w_s[idx] = (r < coc && ci < ci_end) ? op.W[((size_t)(co_grp + co0 + r) * gs_in + (ci - grp * gs_in)) * K + (K - 1 - tf)] : 0.f;
     }
     __syncthreads();
     const float* zb = z_s + wp * 128 + 4 * lane;
@@ -282,7 +292,7 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
   for (int c = 0; c < 8; ++c) {
     const int ci = ci_base + wc * 8 + c;
     float s1 = 0.f, s2 = 0.f;
-    if (ci < op.Cin) {
+    if (ci < ci_end) {
       int cv;
       const int vi = resolve_view(op, ci, cv);
       const SeistView& v = op.in[vi];
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
     float s = 0.f;
     for (int p = 0; p < WP; ++p) s += red_s[(p * WC + w0) * 16 + i];
     const int ci = ci_base + w0 * 8 + (i >> 1);
-    if (ci < op.Cin) {
+    if (ci < ci_end) {
       int cv;
       const int vi = resolve_view(op, ci, cv);
       const SeistView& v = op.in[vi];
@@ -353,7 +363,8 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
 // launchers
 // ================================================================================================
 bool convk_eligible(const SeistOp& op) {
-  if (op.groups != 1 || op.pool > 1 || op.n_in != 1) return false;
+  if (op.pool > 1 || op.n_in != 1) return false;
+  if (op.groups > 1 && ((op.Cin / op.groups) < 8 || (op.Cout / op.groups) < 8)) return false;
   if (op.stride != 1 && op.stride != 2) return false;
   switch (op.k) {
     case 3: case 5: case 7: case 9: case 11: case 13: case 15: case 19: break;
@@ -376,11 +387,12 @@ static int pick_wc(int channels) { return channels > 32 ? 8 : (channels > 16 ? 4
 
 template <int K, int S>
 static int launch_fwd_ks(const SeistOp& op, cudaStream_t s) {
-  const int WC = pick_wc(op.Cout), WP = 8 / WC, CO_B = 8 * WC, TLo = 128 * WP;
+  const int gs_out = op.Cout / op.groups;
+  const int WC = pick_wc(gs_out), WP = 8 / WC, CO_B = 8 * WC, TLo = 128 * WP;
   const int width = TLo * S + K - S, pitch = ((width + 3) & ~3) + 4;
   const size_t smem = sizeof(float) * ((size_t)CK_CIC * pitch + (size_t)CK_CIC * K * CO_B + 8 * 16 +
                                        (op.up_src_L > 0 ? (size_t)CK_CIC * (width + 4) : 0));
-  dim3 grid((op.L_out + TLo - 1) / TLo, op.N, (op.Cout + CO_B - 1) / CO_B);
+  dim3 grid((op.L_out + TLo - 1) / TLo, op.N, op.groups * ((gs_out + CO_B - 1) / CO_B));
   int rc = ck_set_smem(convk_fwd_kernel<K, S>, smem);
   if (rc) return rc;
   convk_fwd_kernel<K, S><<<grid, CK_NT, smem, s>>>(op, WC);
@@ -390,10 +402,11 @@ static int launch_fwd_ks(const SeistOp& op, cudaStream_t s) {
 
 template <int K>
 static int launch_bwdd_k(const SeistOp& op, cudaStream_t s) {
-  const int WC = pick_wc(op.Cin), WP = 8 / WC, CI_B = 8 * WC, TLo = 128 * WP;
+  const int gs_in = op.Cin / op.groups;
+  const int WC = pick_wc(gs_in), WP = 8 / WC, CI_B = 8 * WC, TLo = 128 * WP;
   const int width = TLo + K - 1, pitch = ((width + 3) & ~3) + 4;
   const size_t smem = sizeof(float) * ((size_t)CK_CIC * pitch + (size_t)CK_CIC * K * CI_B + 8 * 16);
-  dim3 grid((op.L_in + TLo - 1) / TLo, op.N, (op.Cin + CI_B - 1) / CI_B);
+  dim3 grid((op.L_in + TLo - 1) / TLo, op.N, op.groups * ((gs_in + CI_B - 1) / CI_B));
   int rc = ck_set_smem(convk_bwd_data_kernel<K>, smem);
   if (rc) return rc;
   convk_bwd_data_kernel<K><<<grid, CK_NT, smem, s>>>(op, WC);

@@ -602,8 +602,13 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
   extern __shared__ __align__(16) unsigned char sm_raw[];
   constexpr int TGM = CO_B / 4, TGN = R_B / 8, TG = TGM * TGN, PG = BW_NT / TG;
   static_assert(TG <= BW_NT && BW_NT % TG == 0, "bad tile");
-  const int k = op.k, S = op.stride, Cin = op.Cin, Cout = op.Cout, L = op.L_out;
-  const int R = Cin * k;
+  const int k = op.k, S = op.stride, L = op.L_out;
+  const int gs_in = op.Cin / op.groups, gs_out = op.Cout / op.groups;
+  const int tpg = (gs_out + CO_B - 1) / CO_B;            // output-channel tiles per group
+  const int grp = blockIdx.y / tpg;
+  const int Cin = (grp + 1) * gs_in;                      // channel bounds of THIS group
+  const int Cout = (grp + 1) * gs_out;
+  const int R = gs_in * k;
   const int width = BW_PC * S + k - S;
   const int pitch = K1 ? BW_PITCH : (width | 1);            // odd pitch: scalar reads spread over banks
   const int stage_f = CO_B * BW_PITCH + nci_max * pitch;
@@ -614,9 +619,9 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
   PwChan* ch_s = reinterpret_cast<PwChan*>(oc_s + CO_B);                // [nci_max] (k = 1 fast path)
   float* src_s = reinterpret_cast<float*>(ch_s + nci_max + 1);          // [nci_max][width+4] (up-sampled input only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int co_base = blockIdx.y * CO_B, r_base = blockIdx.z * R_B;
-  const int ci_lo = r_base / k;
-  const int ci_hi = min((r_base + R_B - 1) / k, Cin - 1);
+  const int co_base = grp * gs_out + (blockIdx.y - grp * tpg) * CO_B, r_base = blockIdx.z * R_B;
+  const int ci_lo = grp * gs_in + r_base / k;
+  const int ci_hi = min(grp * gs_in + (r_base + R_B - 1) / k, Cin - 1);
   const int nci = ci_hi - ci_lo + 1;
 
   for (int col = tid; col < CO_B; col += BW_NT) {
@@ -648,8 +653,8 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
   for (int j = 0; j < 8; ++j) {
     const int r = r_base + tn + TGN * j;          // interleaved columns: lanes of a warp read adjacent rows
     const int rr = r < R ? r : r_base;            // padded columns read valid memory; never written back
-    const int ci = rr / k, t = rr - ci * k;
-    roff[j] = (ci - ci_lo) * pitch + t;
+    const int q = rr / k, t = rr - q * k;               // q: input channel inside the group
+    roff[j] = (grp * gs_in + q - ci_lo) * pitch + t;
   }
   float acc[4][8];
   float bacc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -814,7 +819,7 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
     const int m = tc / TGN, nn = tc % TGN;
     if (e < 32) {
       const int co = co_base + m + TGM * (e >> 3), r = r_base + nn + TGN * (e & 7);
-      if (co < Cout && r < R) atomicAdd(&op.dW[(size_t)co * R + r], s);
+      if (co < Cout && r < R) atomicAdd(&op.dW[(size_t)co * R + r], s);   // W is [Cout][gs_in][k]: row co, column r
     } else if (nn == 0 && blockIdx.z == 0 && op.dbias != nullptr) {
       const int co = co_base + m + TGM * (e - 32);
       if (co < Cout) atomicAdd(&op.dbias[co], s);
@@ -827,15 +832,15 @@ static int launch_bww_pc(const SeistOp& op, cudaStream_t s, int sm_count) {
   constexpr int BW_PITCH = BW_PC + 4;
   const int k = op.k, S = op.stride;
   int nci_max = (R_B + k - 1) / k + 1;
-  if (nci_max > op.Cin) nci_max = op.Cin;
+  if (nci_max > op.Cin / op.groups) nci_max = op.Cin / op.groups;
   const int width = BW_PC * S + k - S;
   const int pitch = K1 ? BW_PITCH : (width | 1);
   int stage_f = CO_B * BW_PITCH + nci_max * pitch;
   if (stage_f < BW_NT * 36) stage_f = BW_NT * 36;
   const size_t smem = sizeof(float) * (size_t)((stage_f + 3) & ~3) + sizeof(PwOut) * CO_B + sizeof(PwChan) * (nci_max + 1) + 64 +
                       (op.up_src_L > 0 ? sizeof(float) * (size_t)nci_max * (width + 4) : 0);
-  const int R = op.Cin * k;
-  const int gy = (op.Cout + CO_B - 1) / CO_B, gz = (R + R_B - 1) / R_B;
+  const int R = (op.Cin / op.groups) * k;
+  const int gy = op.groups * ((op.Cout / op.groups + CO_B - 1) / CO_B), gz = (R + R_B - 1) / R_B;
   const long tiles = (long)op.N * ((op.L_out + BW_PC - 1) / BW_PC);
   long gx = (2L * sm_count + gy * gz - 1) / (gy * gz);
   if (gx > tiles) gx = tiles;
@@ -850,7 +855,7 @@ static int launch_bww_pc(const SeistOp& op, cudaStream_t s, int sm_count) {
 template <int CO_B, int R_B, bool K1>
 static int launch_bww(const SeistOp& op, cudaStream_t s, int sm_count) {
   int nci = (R_B + op.k - 1) / op.k + 1;
-  if (nci > op.Cin) nci = op.Cin;
+  if (nci > op.Cin / op.groups) nci = op.Cin / op.groups;
   // narrow tiles (few rows to stage) and long rows: 512-sample chunks
   if (CO_B <= 16 && nci <= 16 && op.L_out >= 2048 && op.stride == 1) return launch_bww_pc<CO_B, R_B, K1, 512>(op, s, sm_count);
   return launch_bww_pc<CO_B, R_B, K1, 128>(op, s, sm_count);
@@ -858,7 +863,7 @@ static int launch_bww(const SeistOp& op, cudaStream_t s, int sm_count) {
 
 template <bool K1>
 static int launch_bww_sel(const SeistOp& op, cudaStream_t s, int sm_count) {
-  const int co = op.Cout, R = op.Cin * op.k;
+  const int co = op.Cout / op.groups, R = (op.Cin / op.groups) * op.k;
   if (co <= 8) {
     if (R <= 8) return launch_bww<8, 8, K1>(op, s, sm_count);
     if (R <= 16) return launch_bww<8, 16, K1>(op, s, sm_count);
@@ -879,8 +884,8 @@ static int launch_bww_sel(const SeistOp& op, cudaStream_t s, int sm_count) {
 
 // eligibility: dense (groups == 1), single input view unless k == 1, no pooling
 bool bww_eligible(const SeistOp& op) {
-  if (op.groups != 1 || op.pool > 1) return false;
-  if (op.k > 1 && op.n_in != 1) return false;
+  if (op.groups > 1 && ((op.Cin / op.groups) < 8 || (op.Cout / op.groups) < 8)) return false;
+  if ((op.k > 1 || op.pool > 1) && op.n_in != 1) return false;
   return true;
 }
 
