@@ -124,8 +124,8 @@ def main():
     ap.add_argument("--length", type=int, default=8192)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--op-times", default="", help="write the per-op device-time table (JSON) here")
-    ap.add_argument("--cpu-batch", type=int, default=16)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-batch", type=int, default=32)
+    ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -142,8 +142,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 5))
-        warm = max(1, min(args.warmup, 1))
+        steps = max(1, min(args.steps, 20))      # bounded sample: ~0.5 s per 32-waveform CPU step
+        warm = max(1, min(args.warmup, 2))
         rate, secs = cpu_reference_step_rate(args.model, args.cpu_batch, args.length, steps, warm, cores)
         line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
