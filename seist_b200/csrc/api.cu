@@ -47,6 +47,9 @@ bool convk_eligible(const SeistOp& op);
 bool pw_tc_eligible(const SeistOp& op);
 int launch_pw_tc_fwd(const SeistOp& op, cudaStream_t s, int sm_count);
 int pw_tc_error_flag();
+bool bww_tc_eligible(const SeistOp& op);
+int launch_bww_tc(const SeistOp& op, cudaStream_t s, int sm_count);
+int bww_tc_error_flag();
 int launch_convk_fwd(const SeistOp& op, cudaStream_t s);
 int launch_convk_bwd_data(const SeistOp& op, cudaStream_t s);
 int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s);
@@ -93,7 +96,7 @@ static int run_one(const SeistOp& op, cudaStream_t s) {
   switch (op.kind) {
     case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (use_tc(op)) return launch_pw_tc_fwd(op, s, sm_count()); if (pw_eligible(op)) return launch_pw_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
     case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); if (v) return v; if (pw_eligible(op)) return launch_pw_bwd_data(op, s, sm_count()); return (convk_eligible(op) && op.stride == 1) ? launch_convk_bwd_data(op, s) : launch_conv_bwd_data(op, s); }
-    case SEIST_OP_CONV_BWD_W: { int v = validate_conv(op); if (v) return v; return bww_eligible(op) ? launch_bww_any(op, s, sm_count()) : launch_conv_bwd_w(op, s, sm_count()); }
+    case SEIST_OP_CONV_BWD_W: { int v = validate_conv(op); if (v) return v; if (tc_mode() != 0 && bww_tc_eligible(op)) return launch_bww_tc(op, s, sm_count()); return bww_eligible(op) ? launch_bww_any(op, s, sm_count()) : launch_conv_bwd_w(op, s, sm_count()); }
     case SEIST_OP_RES_BWD: return (op.L_out & 3) ? launch_res_bwd(op, s) : launch_res_bwd4(op, s, sm_count());
     case SEIST_OP_ATT_FWD: return launch_att_fwd(op, s);
     case SEIST_OP_ATT_BWD_Q: return launch_att_bwd_q(op, s);
@@ -126,7 +129,7 @@ uint64_t seist_sizeof_op(void) { return sizeof(SeistOp); }
 uint64_t seist_sizeof_bn(void) { return sizeof(SeistBN); }
 const char* seist_last_error(void) { return seist::g_err; }
 uint64_t seist_launch_count(void) { return seist::g_launches.load(); }
-int seist_tc_error_flag(void) { return seist::pw_tc_error_flag(); }
+int seist_tc_error_flag(void) { return seist::pw_tc_error_flag() | seist::bww_tc_error_flag(); }
 
 static std::vector<cudaEvent_t> g_events;
 static cudaEvent_t event_at(size_t i) {
