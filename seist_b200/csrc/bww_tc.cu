@@ -144,35 +144,25 @@ __global__ void __launch_bounds__(BT_NT) bww_tc_kernel(const __grid_constant__ S
 
   // ---- register prefetch of one chunk -------------------------------------------------------------
   float4 pa[BT_MAXQ], pdx[BT_MAXQ], pdu[BT_MAXQ], px[BT_MAXQ];
-  auto load_a = [&](int tile, int u) {
-    const int n = tile / chunks_per_n;
-    const int l0 = (tile - n * chunks_per_n) * BT_KC;
-    const int idx = tid + u * BT_NT;
-    const int row = idx >> 3, q = idx & 7;
-    pa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (idx < items_a && l0 + 4 * q < L) {
-      const BtChan& c = ch_s[row];
-      pa[u] = __ldg(reinterpret_cast<const float4*>(c.x + (long long)n * c.nstride + l0 + 4 * q));
-    }
-  };
-  auto load_b = [&](int tile, int u) {
-    const int n = tile / chunks_per_n;
-    const int l0 = (tile - n * chunks_per_n) * BT_KC;
-    const int idx = tid + u * BT_NT;
-    const int row = idx >> 3, q = idx & 7;
-    pdx[u] = pdu[u] = px[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (idx < items_b && l0 + 4 * q < L) {
-      const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + row) * (size_t)L + l0 + 4 * q;
-      if (op.out_dxd) pdx[u] = __ldg(reinterpret_cast<const float4*>(op.out_dxd + off));
-      if (has_bn) pdu[u] = __ldg(reinterpret_cast<const float4*>(op.out.g + off));
-      if (need_x) px[u] = __ldg(reinterpret_cast<const float4*>(op.out.x + off));
-    }
-  };
   auto prefetch = [&](int tile) {
+    const int n = tile / chunks_per_n;
+    const int l0 = (tile - n * chunks_per_n) * BT_KC;
 #pragma unroll
     for (int u = 0; u < BT_MAXQ; ++u) {
-      load_a(tile, u);
-      load_b(tile, u);
+      const int idx = tid + u * BT_NT;
+      const int row = idx >> 3, q = idx & 7;
+      pa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < items_a && l0 + 4 * q < L) {
+        const BtChan& c = ch_s[row];
+        pa[u] = __ldg(reinterpret_cast<const float4*>(c.x + (long long)n * c.nstride + l0 + 4 * q));
+      }
+      pdx[u] = pdu[u] = px[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < items_b && l0 + 4 * q < L) {
+        const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + row) * (size_t)L + l0 + 4 * q;
+        if (op.out_dxd) pdx[u] = __ldg(reinterpret_cast<const float4*>(op.out_dxd + off));
+        if (has_bn) pdu[u] = __ldg(reinterpret_cast<const float4*>(op.out.g + off));
+        if (need_x) px[u] = __ldg(reinterpret_cast<const float4*>(op.out.x + off));
+      }
     }
   };
 
@@ -195,8 +185,6 @@ __global__ void __launch_bounds__(BT_NT) bww_tc_kernel(const __grid_constant__ S
       parity[s] ^= 1;
     }
     const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
-    const int next_tile = tile + (int)gridDim.x;
-    const bool has_next = next_tile < total;
 #pragma unroll
     for (int u = 0; u < BT_MAXQ; ++u) {
       const int idx = tid + u * BT_NT;
@@ -217,7 +205,6 @@ __global__ void __launch_bounds__(BT_NT) bww_tc_kernel(const __grid_constant__ S
         *reinterpret_cast<float4*>(a_hi + o) = hi;
         *reinterpret_cast<float4*>(a_lo + o) = lo;
       }
-      if (has_next) load_a(next_tile, u);       // this register is free again: fetch the next chunk's value now
       if (idx < items_b) {
         const BtOut oc = oc_s[row];
         float4 g;
@@ -251,7 +238,6 @@ __global__ void __launch_bounds__(BT_NT) bww_tc_kernel(const __grid_constant__ S
         *reinterpret_cast<float4*>(b_hi + o) = hi;
         *reinterpret_cast<float4*>(b_lo + o) = lo;
       }
-      if (has_next) load_b(next_tile, u);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -272,6 +258,7 @@ __global__ void __launch_bounds__(BT_NT) bww_tc_kernel(const __grid_constant__ S
     }
     first = false;
     used[s] += 1;
+    if (tile + (int)gridDim.x < total) prefetch(tile + gridDim.x);
   }
   // ---- drain: all committed MMA batches must have completed before TMEM is read -------------------------
   for (int s = 0; s < 2; ++s) {

@@ -219,9 +219,6 @@ __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant_
       pending = false;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    const bool last_chunk = (chunk + 1 == nchunks);
-    const int nx_tile = last_chunk ? tile + (int)gridDim.x : tile;
-    const int nx_chunk = last_chunk ? 0 : chunk + 1;
     // ---- transform + split + store this thread's sample: canonical K-major [k/8][m/8][(k%8)/4][m%8][k%4] ----
     {
       const bool inb = (l0 + m) < L;
@@ -247,19 +244,6 @@ __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant_
         const int off = (r4 >> 3) * 4096 + (m >> 3) * 256 + ((r4 & 7) >> 2) * 128 + (m & 7) * 16;
         *reinterpret_cast<float4*>(a_hi + off) = hi;
         *reinterpret_cast<float4*>(a_lo + off) = lo;
-        if (nx_tile < total) {          // these four registers are free again: fetch the next step's channels now
-          const int nn = nx_tile / tiles_per_n;
-          const int nlm = (nx_tile - nn * tiles_per_n) * TC_M + m;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int kk = nx_chunk * TC_KC + r4 + j;
-            v[r4 + j] = 0.f;
-            if (kk < Cin && nlm < L) {
-              const TcChan& c = ch_s[kk];
-              v[r4 + j] = __ldg(c.x + (long long)nn * c.nstride + nlm);
-            }
-          }
-        }
       }
     }
     if (!b_resident) stage_b(chunk, 0);
@@ -286,7 +270,11 @@ __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant_
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
     }
     pending = true;
-    const int next_tile = nx_tile, next_chunk = nx_chunk;     // (its loads were issued during the transform above)
+    // ---- next step: issue its global loads now so they fly while the tensor core works -------------------
+    const bool last_chunk = (chunk + 1 == nchunks);
+    const int next_tile = last_chunk ? tile + gridDim.x : tile;
+    const int next_chunk = last_chunk ? 0 : chunk + 1;
+    if (next_tile < total) prefetch(next_tile, next_chunk);
 
     if (last_chunk) {
       if (!tc_wait(bar_addr, parity)) failed = true;

@@ -14,12 +14,7 @@ drops = dict(path_drop_rate=0.2, attn_drop_rate=0.1, key_drop_rate=0.1, mlp_drop
 p_cpu, p_gpu, it, _, _ = build_pair(name, N, L, True, drops)
 torch.manual_seed(1)
 p_cpu.step_seed.fill_(77)
-p_cpu.x_in.x.copy_(torch.randn(N, 3, L))
-p_cpu.stat.zero_()
-for i, fc in enumerate(p_cpu.fwd_ops):          # replay the forward on the GPU too (BN coefficient tables live there)
-    push_state(p_cpu, p_gpu)
-    it.run_fwd_op(fc)
-    run_gpu_op(p_gpu, p_gpu.c_fwd, i)
+it.run_fwd(torch.randn(N, 3, L))
 p_cpu.gstat.zero_(); p_cpu.flat.G.zero_(); p_cpu.dWx.zero_()
 g = torch.Generator().manual_seed(2)
 p_cpu.y_out.dxd.copy_(torch.randn(p_cpu.y_out.dxd.shape, generator=g) / p_cpu.y_out.dxd[0].numel() ** 0.5)
@@ -40,5 +35,6 @@ for i, (bc, bg) in enumerate(zip(p_cpu.bwd_ops, p_gpu.bwd_ops)):
             bs = slice(f.bias.off, f.bias.off + f.bias.numel)
             berr, _ = rel_err(p_gpu.flat.G[bs], p_cpu.flat.G[bs])
         worst = max(worst, err, berr)
-        print(f"SHAPE {f.Cin} {f.Cout} {f.L_out} {'OK' if err < 1e-4 else 'BAD'} {'bOK' if berr < 1e-4 else 'bBAD'}")
+        if err > 1e-4 or berr > 1e-4 or i % 40 == 0:
+            print(f"bwd[{i}] {bc.name:50s} Cin={f.Cin:3d} Cout={f.Cout:3d} L={f.L_out:5d} dW rel_err={err:.2e} dbias={berr:.2e}")
 print("worst", worst, "tc_error_flag", _lib.lib().seist_tc_error_flag())
