@@ -856,8 +856,11 @@ template <int CO_B, int R_B, bool K1>
 static int launch_bww(const SeistOp& op, cudaStream_t s, int sm_count) {
   int nci = (R_B + op.k - 1) / op.k + 1;
   if (nci > op.Cin / op.groups) nci = op.Cin / op.groups;
-  // narrow tiles (few rows to stage) and long rows: 512-sample chunks
-  if (CO_B <= 16 && nci <= 16 && op.L_out >= 2048 && op.stride == 1) return launch_bww_pc<CO_B, R_B, K1, 512>(op, s, sm_count);
+  // longer chunks amortise the per-chunk barriers / exposed load latency wherever the rows are long enough
+  // and the staged tile still fits comfortably: 512 samples for narrow tiles, 256 for medium ones
+  const int rows = CO_B + nci;
+  if (rows <= 32 && op.L_out >= 2048) return launch_bww_pc<CO_B, R_B, K1, 512>(op, s, sm_count);
+  if (rows <= 96 && op.L_out >= 512) return launch_bww_pc<CO_B, R_B, K1, 256>(op, s, sm_count);
   return launch_bww_pc<CO_B, R_B, K1, 128>(op, s, sm_count);
 }
 
