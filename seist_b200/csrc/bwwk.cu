@@ -1,0 +1,305 @@
+// Weight gradient of the dense k-tap convolutions (k > 1): composed stem paths, MSMC branches, the dpk head
+// (reference models/seist.py:86-111 stem, :225-287 MSMC, :566-575 head up-sampling + conv).
+//
+//   dW[co][ci][t] = sum_{n,l} gacc[co][n,l] * convin[ci][n, l*S + t - pad_left]
+//
+// Sliding-window formulation: a thread owns 4 output channels x ONE input channel x all K taps.  For a quad
+// of 4 consecutive output samples it reads the 4 gacc quads (broadcast across the lanes that share the
+// channel group) and the K+3S input samples the quad touches as ceil((K+3S)/4) 16-byte shared loads, then
+// issues 16*K FMAs - the taps of one input channel re-use the same window out of registers instead of
+// re-reading it once per tap as the row-tiled kernel in pw.cu does (k = 7: 112 FMA per 7 LDS.128).
+//
+// A CTA owns a (4*TGM) x CI_B tile of (co, ci) pairs and a strided share of the PC-sample chunks of all
+// waveforms.  Per chunk every gacc / input element is loaded and transformed ONCE into shared memory
+// (BN-backward prologue for gacc; BN-apply / GELU / up-sampling / zero padding for the input).  Threads are
+// laid out as TG = TGM*nci tile coordinates x PG sample groups; the sample groups are folded through shared
+// memory at the end, one float atomic per dW element per CTA.
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace seist {
+
+constexpr int BK_NT = 256;
+
+namespace {
+__device__ __forceinline__ float4 bk_ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 bk_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void bk_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+struct BkOut {
+  float A, Bx, Cc, pad;
+};
+}  // namespace
+
+template <int K, int S, int TGM>
+__global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ SeistOp op, const int CI_B, const int PC,
+                                                        const int pitch, const int area_f) {
+  constexpr int CO_B = 4 * TGM;
+  constexpr int WN = K + 3 * S, WQ = (WN + 3) / 4;
+  constexpr int RW = (K + 1) | 1;                      // odd row pitch of the final fold
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int L = op.L_out;
+  const int gpitch = PC + 4;
+  const int gs_in = op.Cin / op.groups, gs_out = op.Cout / op.groups;
+  const int tpg = (gs_out + CO_B - 1) / CO_B;            // output-channel tiles per group
+  const int grp = blockIdx.y / tpg;
+  const int Cin_hi = (grp + 1) * gs_in, Cout_hi = (grp + 1) * gs_out;
+  const int width = PC * S + K - S;
+  float* g_s = reinterpret_cast<float*>(sm_raw);          // [CO_B][gpitch]
+  float* in_s = g_s + CO_B * gpitch;                      // [CI_B][pitch]
+  BkOut* oc_s = reinterpret_cast<BkOut*>(g_s + area_f);   // [CO_B]
+  float* src_s = reinterpret_cast<float*>(oc_s + CO_B);   // [CI_B][width+4] (up-sampled input only)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int co_base = grp * gs_out + (blockIdx.y - grp * tpg) * CO_B;
+  const int ci_lo = grp * gs_in + blockIdx.z * CI_B;
+  const int nci = min(CI_B, Cin_hi - ci_lo);
+
+  for (int col = tid; col < CO_B; col += BK_NT) {
+    const int co = co_base + col;
+    BkOut o = {0.f, 0.f, 0.f, 0.f};
+    if (co < Cout_hi) {
+      const OutGradCoef kc = out_grad_coef(op, co);
+      o.A = kc.A;
+      o.Bx = kc.Bx;
+      o.Cc = kc.Cc;
+    }
+    oc_s[col] = o;
+  }
+  __syncthreads();
+
+  const uint64_t seed = load_seed(op.step_seed);
+  const bool has_bn = (op.out.bn >= 0 && op.out.g != nullptr);
+  const bool need_x = has_bn || op.out_act == SEIST_OUT_SIGMOID;
+  const int Lsrc = op.in[0].L;
+  const float ratio = op.up_src_L > 0 ? (float)Lsrc / (float)op.L_in : 1.f;
+  const int TG = TGM * nci, PG = BK_NT / TG;
+  const int tcoord = tid % TG, pg = tid / TG;
+  const bool active = pg < PG;
+  const int tm = tcoord / nci, tn = tcoord - tm * nci;
+  const float* my_in = in_s + tn * pitch;
+  const float* my_g = g_s + tm * gpitch;
+
+  float acc[4][K];
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int t = 0; t < K; ++t) acc[i][t] = 0.f;
+
+  const int chunks_per_n = (L + PC - 1) / PC;
+  const int total = op.N * chunks_per_n;
+  const int QPR = PC >> 2;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = tile / chunks_per_n;
+    const int l0 = (tile - n * chunks_per_n) * PC;
+    const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
+    // ---- gacc rows ------------------------------------------------------------------------------
+    for (int idx = tid; idx < CO_B * QPR; idx += BK_NT) {
+      const int row = idx / QPR, q = idx - row * QPR;
+      const int co = co_base + row, l = l0 + 4 * q;
+      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co < Cout_hi && l < L) {
+        const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l;
+        if (op.out_dxd) gv = bk_ldg4(op.out_dxd + off);
+        if (need_x) {
+          const float4 x = bk_ldg4(op.out.x + off);
+          if (has_bn) {
+            const float4 du = bk_ldg4(op.out.g + off);
+            const BkOut o = oc_s[row];
+            gv.x += fmaf(o.A, du.x, fmaf(o.Bx, x.x, o.Cc));
+            gv.y += fmaf(o.A, du.y, fmaf(o.Bx, x.y, o.Cc));
+            gv.z += fmaf(o.A, du.z, fmaf(o.Bx, x.z, o.Cc));
+            gv.w += fmaf(o.A, du.w, fmaf(o.Bx, x.w, o.Cc));
+          }
+          if (op.out_act == SEIST_OUT_SIGMOID) {
+            gv.x *= x.x * (1.f - x.x);
+            gv.y *= x.y * (1.f - x.y);
+            gv.z *= x.z * (1.f - x.z);
+            gv.w *= x.w * (1.f - x.w);
+          }
+        }
+        gv.x *= pf;
+        gv.y *= pf;
+        gv.z *= pf;
+        gv.w *= pf;
+        if (op.p_elem > 0.f) {
+          const uint64_t e = ((uint64_t)n * op.Cout + co) * (uint64_t)L + l;
+          gv.x *= keep_scale(op.p_elem, seed, op.seed_elem, e);
+          gv.y *= keep_scale(op.p_elem, seed, op.seed_elem, e + 1);
+          gv.z *= keep_scale(op.p_elem, seed, op.seed_elem, e + 2);
+          gv.w *= keep_scale(op.p_elem, seed, op.seed_elem, e + 3);
+        }
+      }
+      bk_st4(g_s + row * gpitch + 4 * q, gv);
+    }
+    // ---- conv-input rows: in_s[r][pos] <-> conv-input coordinate p_base + pos ----------------------
+    const int p_base = l0 * S - op.pad_left;
+    if (op.up_src_L > 0) {
+      stage_upsampled_rows(op, n, ci_lo, nci, in_s, pitch, width, p_base, src_s, width + 4, Lsrc, ratio);
+    } else {
+      for (int r = warp; r < nci; r += BK_NT / 32) {
+        const RowSrc rs = make_row(op, n, ci_lo + r);
+        float* dst = in_s + r * pitch;
+        for (int pos0 = lane; pos0 < width; pos0 += 32 * 4) {
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int p = p_base + pos0 + 32 * u;
+            v[u] = (pos0 + 32 * u < width && p >= 0 && p < op.L_in) ? rs.x[p] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int pos = pos0 + 32 * u, p = p_base + pos;
+            if (pos < width) {
+              float t = fmaf(rs.sc, v[u], rs.sh);
+              if (rs.act == SEIST_ACT_GELU) t = gelu_f(t);
+              dst[pos] = (p >= 0 && p < op.L_in) ? t : 0.f;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- accumulate -------------------------------------------------------------------------------
+    if (active) {
+      for (int q = pg; q < QPR; q += PG) {
+        float w[4 * WQ];
+        const float* ip = my_in + 4 * q * S;
+#pragma unroll
+        for (int j = 0; j < WQ; ++j) {
+          const float4 t4 = bk_ld4(ip + 4 * j);
+          w[4 * j] = t4.x;
+          w[4 * j + 1] = t4.y;
+          w[4 * j + 2] = t4.z;
+          w[4 * j + 3] = t4.w;
+        }
+        float4 gq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gq[i] = bk_ld4(my_g + TGM * i * gpitch + 4 * q);
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float a = acc[i][t];
+            a = fmaf(gq[i].x, w[t], a);
+            a = fmaf(gq[i].y, w[S + t], a);
+            a = fmaf(gq[i].z, w[2 * S + t], a);
+            a = fmaf(gq[i].w, w[3 * S + t], a);
+            acc[i][t] = a;
+          }
+        }
+        if (tn == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) bacc[i] += (gq[i].x + gq[i].y) + (gq[i].z + gq[i].w);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- fold the sample groups through shared memory, one channel group (i) per round --------------------
+  float* red = g_s;
+  const int R = gs_in * K;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float* mine = red + (size_t)tid * RW;
+#pragma unroll
+    for (int t = 0; t < K; ++t) mine[t] = acc[i][t];
+    mine[K] = bacc[i];
+    __syncthreads();
+    for (int idx = tid; idx < TG * (K + 1); idx += BK_NT) {
+      const int tc = idx / (K + 1), e = idx - tc * (K + 1);
+      float s = 0.f;
+      for (int p = 0; p < PG; ++p) s += red[((size_t)p * TG + tc) * RW + e];
+      const int m = tc / nci, cr = tc - m * nci;
+      const int co = co_base + m + TGM * i;
+      if (co < Cout_hi) {
+        if (e < K) {
+          atomicAdd(&op.dW[(size_t)co * R + (size_t)(ci_lo - grp * gs_in + cr) * K + e], s);
+        } else if (cr == 0 && blockIdx.z == 0 && op.dbias != nullptr) {
+          atomicAdd(&op.dbias[co], s);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int K, int S, int TGM>
+static int launch_bwwk_t(const SeistOp& op, cudaStream_t s, int sm_count) {
+  constexpr int CO_B = 4 * TGM;
+  constexpr int WQ = (K + 3 * S + 3) / 4;
+  constexpr int RW = (K + 1) | 1;
+  const int gs_in = op.Cin / op.groups, gs_out = op.Cout / op.groups;
+  const int ntile = (gs_in + 15) / 16;
+  const int CI_B = (gs_in + ntile - 1) / ntile;          // balanced input-channel tiles of at most 16
+  int PC = 128;
+  if (op.L_out >= 2048 && CO_B + CI_B <= 24) PC = 512;
+  else if (op.L_out >= 256) PC = 256;
+  if (PC > ((op.L_out + 3) & ~3)) PC = (op.L_out + 3) & ~3;
+  const int width = PC * S + K - S;
+  // row pitch: room for the last quad's window over-read, 16-byte aligned, = 4 (mod 32) so that the 8 lanes
+  // of a quarter warp reading 8 different rows hit 8 different 16-byte bank groups
+  int pitch = (4 * (PC / 4 - 1) * S + 4 * WQ + 3) & ~3;
+  if (pitch < ((width + 3) & ~3)) pitch = (width + 3) & ~3;
+  while ((pitch & 31) != 4) pitch += 4;
+  int area_f = CO_B * (PC + 4) + CI_B * pitch;
+  if (area_f < BK_NT * RW) area_f = BK_NT * RW;
+  area_f = (area_f + 3) & ~3;
+  const size_t smem = sizeof(float) * (size_t)area_f + sizeof(BkOut) * CO_B +
+                      (op.up_src_L > 0 ? sizeof(float) * (size_t)CI_B * (width + 4) : 0) + 16;
+  const int gy = op.groups * ((gs_out + CO_B - 1) / CO_B), gz = ntile;
+  const long tiles = (long)op.N * ((op.L_out + PC - 1) / PC);
+  long gx = (2L * sm_count + gy * gz - 1) / (gy * gz);
+  if (gx > tiles) gx = tiles;
+  if (gx < 1) gx = 1;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(bwwk_kernel<K, S, TGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  bwwk_kernel<K, S, TGM><<<dim3((unsigned)gx, gy, gz), BK_NT, smem, s>>>(op, CI_B, PC, pitch, area_f);
+  note_launch();
+  return check_launch("bwwk");
+}
+
+template <int K, int S>
+static int launch_bwwk_ks(const SeistOp& op, cudaStream_t s, int sm_count) {
+  if (op.Cout / op.groups <= 8) return launch_bwwk_t<K, S, 2>(op, s, sm_count);
+  return launch_bwwk_t<K, S, 4>(op, s, sm_count);
+}
+
+static bool bwwk_has(int k, int stride) {
+  if (stride == 1) return k == 3 || k == 5 || k == 7 || k == 9 || k == 11 || k == 13;
+  if (stride == 2) return k == 7 || k == 11 || k == 15 || k == 19;
+  return false;
+}
+
+// eligibility: one input view, no pooling, whole quads, a compiled (k, stride) pair
+bool bwwk_eligible(const SeistOp& op) {
+  if (op.n_in != 1 || op.pool > 1 || (op.L_out & 3)) return false;
+  if (op.Cin % op.groups || op.Cout % op.groups) return false;
+  return bwwk_has(op.k, op.stride);
+}
+
+int launch_bwwk(const SeistOp& op, cudaStream_t s, int sm_count) {
+  if (op.stride == 1) {
+    switch (op.k) {
+      case 3: return launch_bwwk_ks<3, 1>(op, s, sm_count);
+      case 5: return launch_bwwk_ks<5, 1>(op, s, sm_count);
+      case 7: return launch_bwwk_ks<7, 1>(op, s, sm_count);
+      case 9: return launch_bwwk_ks<9, 1>(op, s, sm_count);
+      case 11: return launch_bwwk_ks<11, 1>(op, s, sm_count);
+      case 13: return launch_bwwk_ks<13, 1>(op, s, sm_count);
+    }
+  } else if (op.stride == 2) {
+    switch (op.k) {
+      case 7: return launch_bwwk_ks<7, 2>(op, s, sm_count);
+      case 11: return launch_bwwk_ks<11, 2>(op, s, sm_count);
+      case 15: return launch_bwwk_ks<15, 2>(op, s, sm_count);
+      case 19: return launch_bwwk_ks<19, 2>(op, s, sm_count);
+    }
+  }
+  set_error("bwwk: no kernel compiled for this (k, stride)");
+  return -1;
+}
+
+}  // namespace seist

@@ -250,7 +250,7 @@ struct PwOut {   // per output channel of the forward op, resolved once per CTA
 };
 
 template <int CI_T, bool F_ELEM, bool F_GELU>
-__global__ void __launch_bounds__(PW_NT) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G) {
+__global__ void __launch_bounds__(PW_NT, 3) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cout = op.Cout, Cout4 = (Cout + 3) & ~3, Cin = op.Cin;
   PwChan* ch_s = reinterpret_cast<PwChan*>(sm_raw);                       // [CI_T] targets
