@@ -50,6 +50,7 @@ int pw_tc_error_flag();
 bool bww_tc_eligible(const SeistOp& op);
 int launch_bww_tc(const SeistOp& op, cudaStream_t s, int sm_count);
 bool bwwk_eligible(const SeistOp& op);
+bool convk_bwd_data_eligible(const SeistOp& op);
 int launch_bwwk(const SeistOp& op, cudaStream_t s, int sm_count);
 int bww_tc_error_flag();
 int launch_convk_fwd(const SeistOp& op, cudaStream_t s);
@@ -103,7 +104,7 @@ static int validate_conv(const SeistOp& op) {
 static int run_one(const SeistOp& op, cudaStream_t s) {
   switch (op.kind) {
     case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (use_tc(op)) return launch_pw_tc_fwd(op, s, sm_count()); if (pw_eligible(op)) return launch_pw_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
-    case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); if (v) return v; if (pw_eligible(op)) return launch_pw_bwd_data(op, s, sm_count()); return (convk_eligible(op) && op.stride == 1) ? launch_convk_bwd_data(op, s) : launch_conv_bwd_data(op, s); }
+    case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); if (v) return v; if (pw_eligible(op)) return launch_pw_bwd_data(op, s, sm_count()); return convk_bwd_data_eligible(op) ? launch_convk_bwd_data(op, s) : launch_conv_bwd_data(op, s); }
     case SEIST_OP_CONV_BWD_W: { int v = validate_conv(op); if (v) return v; if (tc_mode() == 1 && bww_tc_eligible(op)) return launch_bww_tc(op, s, sm_count()); /* validated; opt-in (SEIST_TC=1) until it beats the SIMT kernel */ if (bwwk_mode() && bwwk_eligible(op)) return launch_bwwk(op, s, sm_count()); return bww_eligible(op) ? launch_bww_any(op, s, sm_count()) : launch_conv_bwd_w(op, s, sm_count()); }
     case SEIST_OP_RES_BWD: return (op.L_out & 3) ? launch_res_bwd(op, s) : launch_res_bwd4(op, s, sm_count());
     case SEIST_OP_ATT_FWD: return launch_att_fwd(op, s);

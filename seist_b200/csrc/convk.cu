@@ -212,12 +212,20 @@ __global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant_
 }
 
 // ================================================================================================
-// backward (data), stride 1:  d in[ci][p] = sum_{co,t} W[co][ci][t] gacc[co][p + pad_left - t]
+// backward (data):  d in[ci][p] = sum_{co,t} W[co][ci][t] gacc[co][(p + pad_left - t) / S]
+//   S = 1: the forward engine over the combined output gradient with flipped/transposed weights.
+//   S = 2 (pad_left even): input positions split by parity, p = 2u + r.  Parity r only meets the taps
+//     t = r + 2s, so each parity is a stride-1 correlation of gacc with a sub-filter of KE = (K+1)/2 taps
+//     (the odd one padded with a zero tap so that both share one window): the engine runs with 8 "virtual"
+//     channels per warp = 4 input channels x 2 parities, and a thread that owns 4 consecutive u writes 8
+//     consecutive input samples per channel.
 // ================================================================================================
-template <int K>
+template <int K, int S>
 __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_constant__ SeistOp op, const int WC) {
   extern __shared__ __align__(16) float ck_smem[];
-  const int WP = 8 / WC, CI_B = 8 * WC, TLo = 128 * WP;
+  constexpr int KE = S == 2 ? (K + 1) / 2 : K;          // taps of the stride-1 engine
+  constexpr int CPW = S == 2 ? 4 : 8;                   // real input channels per warp
+  const int WP = 8 / WC, CI_B = CPW * WC, VC_B = 8 * WC, TLo = 128 * WP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wc = warp % WC, wp = warp / WC;
   const int gs_in = op.Cin / op.groups, gs_out = op.Cout / op.groups;
@@ -226,14 +234,14 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
   const int n = blockIdx.y, p0 = blockIdx.x * TLo, ci_base = grp * gs_in + (blockIdx.z - grp * tpg) * CI_B;
   const int ci_end = (grp + 1) * gs_in;
   const int co_grp = grp * gs_out;
-  const int width = TLo + K - 1;
+  const int width = TLo + KE - 1;
   const int pitch = ((width + 3) & ~3) + 4;
   float* z_s = ck_smem;                                // [CIC][pitch]
-  float* w_s = ck_smem + CK_CIC * pitch;               // [CIC][K][CI_B]
-  float* red_s = w_s + CK_CIC * K * CI_B;              // [8][16]
+  float* w_s = ck_smem + CK_CIC * pitch;               // [CIC][KE][VC_B]
+  float* red_s = w_s + CK_CIC * KE * VC_B;             // [8][16]
   const uint64_t seed = load_seed(op.step_seed);
   const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
-  const int m_base = p0 + op.pad_left - (K - 1);       // output-sample coordinate of z_s[.][0]
+  const int m_base = p0 + op.pad_left / S - (KE - 1);  // output-sample coordinate of z_s[.][0]
 
   float acc[8][4];
 #pragma unroll
@@ -269,17 +277,18 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
         }
       }
     }
-    // flipped + transposed weights: w_s[(r*K + tf)*CI_B + col] = W[co0+r][ci_base+col][K-1-tf]
-    for (int idx = tid; idx < CK_CIC * K * CI_B; idx += CK_NT) {
-      const int col = idx % CI_B, rest = idx / CI_B;
-      const int tf = rest % K, r = rest / K;
-      const int ci = ci_base + col;
-      w_s[idx] = (r < coc && ci < ci_end) ? op.W[((size_t)(co_grp + co0 + r) * gs_in + (ci - grp * gs_in)) * K + (K - 1 - tf)] : 0.f;
+    // flipped + transposed weights: w_s[(r*KE + tf)*VC_B + col] = W[co0+r][ci(col)][t(tf, parity(col))]
+    for (int idx = tid; idx < CK_CIC * KE * VC_B; idx += CK_NT) {
+      const int col = idx % VC_B, rest = idx / VC_B;
+      const int tf = rest % KE, r = rest / KE;
+      const int ci = ci_base + (S == 2 ? (col >> 1) : col);
+      const int t = S == 2 ? (col & 1) + 2 * (KE - 1 - tf) : (K - 1 - tf);
+      w_s[idx] = (r < coc && ci < ci_end && t < K) ? op.W[((size_t)(co_grp + co0 + r) * gs_in + (ci - grp * gs_in)) * K + t] : 0.f;
     }
     __syncthreads();
     const float* zb = z_s + wp * 128 + 4 * lane;
     const float* wb = w_s + wc * 8;
-    for (int r = 0; r < coc; ++r) ck_accumulate<K, 1>(zb + r * pitch, wb + r * K * CI_B, CI_B, acc);
+    for (int r = 0; r < coc; ++r) ck_accumulate<KE, 1>(zb + r * pitch, wb + r * KE * VC_B, VC_B, acc);
     __syncthreads();
   }
 
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
   float st[16];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const int ci = ci_base + wc * 8 + c;
+    const int ci = ci_base + wc * CPW + (S == 2 ? (c >> 1) : c);
     float s1 = 0.f, s2 = 0.f;
     if (ci < ci_end) {
       int cv;
@@ -304,7 +313,7 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
         float* gr = view_grad_row(v, n, cv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int p = pq + j;
+          const int p = S == 2 ? 2 * (pq + j) + (c & 1) : pq + j;
           if (p >= op.L_in) continue;
           const float d = acc[c][j];
           if (op.up_src_L > 0) {
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
     const int w0 = idx / 16, i = idx % 16;
     float s = 0.f;
     for (int p = 0; p < WP; ++p) s += red_s[(p * WC + w0) * 16 + i];
-    const int ci = ci_base + w0 * 8 + (i >> 1);
+    const int ci = ci_base + w0 * CPW + (S == 2 ? (i >> 2) : (i >> 1));
     if (ci < ci_end) {
       int cv;
       const int vi = resolve_view(op, ci, cv);
@@ -400,16 +409,18 @@ static int launch_fwd_ks(const SeistOp& op, cudaStream_t s) {
   return check_launch("convk_fwd");
 }
 
-template <int K>
+template <int K, int S>
 static int launch_bwdd_k(const SeistOp& op, cudaStream_t s) {
+  constexpr int KE = S == 2 ? (K + 1) / 2 : K;
+  constexpr int CPW = S == 2 ? 4 : 8;
   const int gs_in = op.Cin / op.groups;
-  const int WC = pick_wc(gs_in), WP = 8 / WC, CI_B = 8 * WC, TLo = 128 * WP;
-  const int width = TLo + K - 1, pitch = ((width + 3) & ~3) + 4;
-  const size_t smem = sizeof(float) * ((size_t)CK_CIC * pitch + (size_t)CK_CIC * K * CI_B + 8 * 16);
-  dim3 grid((op.L_in + TLo - 1) / TLo, op.N, op.groups * ((gs_in + CI_B - 1) / CI_B));
-  int rc = ck_set_smem(convk_bwd_data_kernel<K>, smem);
+  const int WC = pick_wc(gs_in * (8 / CPW)), WP = 8 / WC, CI_B = CPW * WC, TLo = 128 * WP;
+  const int width = TLo + KE - 1, pitch = ((width + 3) & ~3) + 4;
+  const size_t smem = sizeof(float) * ((size_t)CK_CIC * pitch + (size_t)CK_CIC * KE * 8 * WC + 8 * 16);
+  dim3 grid(((op.L_in + S - 1) / S + TLo - 1) / TLo, op.N, op.groups * ((gs_in + CI_B - 1) / CI_B));
+  int rc = ck_set_smem(convk_bwd_data_kernel<K, S>, smem);
   if (rc) return rc;
-  convk_bwd_data_kernel<K><<<grid, CK_NT, smem, s>>>(op, WC);
+  convk_bwd_data_kernel<K, S><<<grid, CK_NT, smem, s>>>(op, WC);
   note_launch();
   return check_launch("convk_bwd_data");
 }
@@ -440,8 +451,23 @@ int launch_convk_fwd(const SeistOp& op, cudaStream_t s) {
 #undef FWD1
 }
 
+// stride 2 needs an even left pad and no up-sampling (true for every strided conv of the model family)
+bool convk_bwd_data_eligible(const SeistOp& op) {
+  if (!convk_eligible(op)) return false;
+  if (op.stride == 1) return true;
+  return (op.pad_left & 1) == 0 && op.up_src_L == 0;
+}
+
 int launch_convk_bwd_data(const SeistOp& op, cudaStream_t s) {
-#define BD(KK, dummy) launch_bwdd_k<KK>(op, s)
+  if (op.stride == 2) {
+    switch (op.k) {
+      case 7: return launch_bwdd_k<7, 2>(op, s);
+      case 11: return launch_bwdd_k<11, 2>(op, s);
+      case 15: return launch_bwdd_k<15, 2>(op, s);
+      default: return launch_bwdd_k<19, 2>(op, s);
+    }
+  }
+#define BD(KK, dummy) launch_bwdd_k<KK, 1>(op, s)
   CK_SWITCH_K(BD, 0)
 #undef BD
 }
