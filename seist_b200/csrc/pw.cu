@@ -101,13 +101,14 @@ __device__ __noinline__ float4 pw_keep4(float p, uint64_t seed, uint32_t stream,
 // compile-time specialisation keeps the bodies small (instruction cache) and the inner loops free of
 // runtime feature tests: F_ELEM element dropout, F_RES residual views, F_GELU some view applies GELU
 template <int COUT_T, bool F_ELEM, bool F_RES, bool F_GELU>
-__global__ void __launch_bounds__(PW_NT) pw_fwd_kernel(const __grid_constant__ SeistOp op, const int G) {
+__global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant__ SeistOp op, const int G) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cin = op.Cin, Cin8 = (Cin + 7) & ~7;
   PwChan* ch_s = reinterpret_cast<PwChan*>(sm_raw);                       // [Cin8]
   float* w_s = reinterpret_cast<float*>(ch_s + Cin8);                     // [Cin8][COUT_T]
   float* ep_s = w_s + Cin8 * COUT_T;                                      // bias, ra_sc, ra_sh, rb_sc, rb_sh [COUT_T] each
   float* red_s = ep_s + 5 * COUT_T;                                       // [4][2*COUT_T]
+  float* st_s = red_s + 4 * 2 * COUT_T;                                   // [4 warps][2*COUT_T][32 lanes] running sums
   const int tid = threadIdx.x;
   const int co_base = blockIdx.y * COUT_T;
   const int L = op.L_out, LQ = L >> 2;
@@ -145,9 +146,11 @@ __global__ void __launch_bounds__(PW_NT) pw_fwd_kernel(const __grid_constant__ S
   const uint64_t seed = load_seed(op.step_seed);
   const long long NQ = (long long)op.N * LQ;
   const bool stats = (op.out.bn >= 0) && op.bn_table[op.out.bn >= 0 ? op.out.bn : 0].use_batch;
-  float st[2 * COUT_T];
+  // BatchNorm sums of the result live in shared memory (one private slot per thread and statistic) between
+  // quads: in registers they would cost 2*COUT_T registers across the whole contraction loop
+  float* my_st = st_s + (tid >> 5) * (2 * COUT_T * 32) + (tid & 31);
 #pragma unroll
-  for (int i = 0; i < 2 * COUT_T; ++i) st[i] = 0.f;
+  for (int i = 0; i < 2 * COUT_T; ++i) my_st[i * 32] = 0.f;
 
   for (int g = 0; g < G; ++g) {
     const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
@@ -226,11 +229,16 @@ __global__ void __launch_bounds__(PW_NT) pw_fwd_kernel(const __grid_constant__ S
         r.w = sigmoid_f(r.w);
       }
       st4(op.out.x + ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l, r);
-      st[2 * col] += (r.x + r.y) + (r.z + r.w);
-      st[2 * col + 1] += fmaf(r.x, r.x, r.y * r.y) + fmaf(r.z, r.z, r.w * r.w);
+      if (stats) {
+        my_st[(2 * col) * 32] += (r.x + r.y) + (r.z + r.w);
+        my_st[(2 * col + 1) * 32] += fmaf(r.x, r.x, r.y * r.y) + fmaf(r.z, r.z, r.w * r.w);
+      }
     }
   }
   if (stats) {
+    float st[2 * COUT_T];
+#pragma unroll
+    for (int i = 0; i < 2 * COUT_T; ++i) st[i] = my_st[i * 32];
     cta_reduce_atomic<2 * COUT_T>(st, red_s, [&](int i, float s) {
       const int co = co_base + (i >> 1);
       if (co < op.Cout) {
@@ -245,18 +253,20 @@ __global__ void __launch_bounds__(PW_NT) pw_fwd_kernel(const __grid_constant__ S
 // backward (data): d in[ci] = sum_co W[co][ci] gacc[co];  gacc = dOut * alpha * delta * D
 // dOut = A*du + Bx*x + Cc + dxd (then sigmoid').  grid (ceil(NQ/(128*G)), ceil(Cin/CI_T))
 // ================================================================================================
+constexpr int PW_BD_CG = 2;   // output channels whose gradient loads are in flight together (register budget: 4 CTAs/SM)
 struct PwOut {   // per output channel of the forward op, resolved once per CTA
   float A, Bx, Cc;
 };
 
 template <int CI_T, bool F_ELEM, bool F_GELU>
-__global__ void __launch_bounds__(PW_NT, 3) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G) {
+__global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cout = op.Cout, Cout4 = (Cout + 3) & ~3, Cin = op.Cin;
   PwChan* ch_s = reinterpret_cast<PwChan*>(sm_raw);                       // [CI_T] targets
   PwOut* oc_s = reinterpret_cast<PwOut*>(ch_s + CI_T);                    // [Cout4]
   float* w_s = reinterpret_cast<float*>(oc_s + Cout4);                    // [Cout4][CI_T]
   float* red_s = w_s + Cout4 * CI_T;                                      // [4][2*CI_T]
+  float* st_s = red_s + 4 * 2 * CI_T;                                     // [4 warps][2*CI_T][32 lanes] running sums
   const int tid = threadIdx.x;
   const int ci_base = blockIdx.y * CI_T;
   const int L = op.L_out, LQ = L >> 2;
@@ -288,9 +298,11 @@ __global__ void __launch_bounds__(PW_NT, 3) pw_bwd_data_kernel(const __grid_cons
   const long long NQ = (long long)op.N * LQ;
   const bool has_bn = (op.out.bn >= 0 && op.out.g != nullptr);
   const bool need_x = has_bn || op.out_act == SEIST_OUT_SIGMOID;
-  float st[2 * CI_T];
+  // BN-backward sums of the targets live in shared memory (one private slot per thread and statistic)
+  // between quads: keeping them in registers costs 2*CI_T registers across the whole contraction loop
+  float* my_st = st_s + (tid >> 5) * (2 * CI_T * 32) + (tid & 31);
 #pragma unroll
-  for (int i = 0; i < 2 * CI_T; ++i) st[i] = 0.f;
+  for (int i = 0; i < 2 * CI_T; ++i) my_st[i * 32] = 0.f;
 
   for (int g = 0; g < G; ++g) {
     const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
@@ -302,10 +314,10 @@ __global__ void __launch_bounds__(PW_NT, 3) pw_bwd_data_kernel(const __grid_cons
 #pragma unroll
     for (int c = 0; c < CI_T; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t obase = ((size_t)n * op.out.Ct + op.out.c0) * (size_t)L + l;
-    for (int co0 = 0; co0 < Cout4; co0 += 4) {
-      float4 dx[4], du[4], xo[4];
+    for (int co0 = 0; co0 < Cout4; co0 += PW_BD_CG) {
+      float4 dx[PW_BD_CG], du[PW_BD_CG], xo[PW_BD_CG];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < PW_BD_CG; ++j) {
         const int co = min(co0 + j, Cout - 1);
         const size_t off = obase + (size_t)co * L;
         dx[j] = op.out_dxd ? ldg4(op.out_dxd + off) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -313,7 +325,7 @@ __global__ void __launch_bounds__(PW_NT, 3) pw_bwd_data_kernel(const __grid_cons
         xo[j] = need_x ? ldg4(op.out.x + off) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < PW_BD_CG; ++j) {
         const int co = co0 + j;
         const PwOut o = oc_s[co];
         float4 gv;
@@ -367,9 +379,9 @@ __global__ void __launch_bounds__(PW_NT, 3) pw_bwd_data_kernel(const __grid_cons
         gg.w *= d.w;
       }
       if (c.bn >= 0) {
-        st[2 * col] += (gg.x + gg.y) + (gg.z + gg.w);
-        st[2 * col + 1] += fmaf(gg.x, (x.x - c.mu) * c.istd, gg.y * ((x.y - c.mu) * c.istd)) +
-                           fmaf(gg.z, (x.z - c.mu) * c.istd, gg.w * ((x.w - c.mu) * c.istd));
+        my_st[(2 * col) * 32] += (gg.x + gg.y) + (gg.z + gg.w);
+        my_st[(2 * col + 1) * 32] += fmaf(gg.x, (x.x - c.mu) * c.istd, gg.y * ((x.y - c.mu) * c.istd)) +
+                                     fmaf(gg.z, (x.z - c.mu) * c.istd, gg.w * ((x.w - c.mu) * c.istd));
       }
       float* gp = c.g + off;
       if (c.accum) {
@@ -382,6 +394,9 @@ __global__ void __launch_bounds__(PW_NT, 3) pw_bwd_data_kernel(const __grid_cons
       st4(gp, gg);
     }
   }
+  float st[2 * CI_T];
+#pragma unroll
+  for (int i = 0; i < 2 * CI_T; ++i) st[i] = my_st[i * 32];
   cta_reduce_atomic<2 * CI_T>(st, red_s, [&](int i, float s) {
     const PwChan& c = ch_s[i >> 1];
     if (c.g != nullptr && c.bn >= 0) {
@@ -531,7 +546,7 @@ static int pw_fwd_sel(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem,
 int launch_pw_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int cot = op.Cout > 8 ? 16 : 8;
   const int Cin8 = (op.Cin + 7) & ~7;
-  const size_t smem = sizeof(PwChan) * Cin8 + sizeof(float) * ((size_t)Cin8 * cot + 5 * cot + 4 * 2 * cot);
+  const size_t smem = sizeof(PwChan) * Cin8 + sizeof(float) * ((size_t)Cin8 * cot + 5 * cot + 4 * 2 * cot + 4 * 2 * cot * 32);
   const long long nq = (long long)op.N * (op.L_out >> 2);
   const int ty = (op.Cout + cot - 1) / cot;
   const int G = pick_G(nq, ty, sm_count);
@@ -562,7 +577,7 @@ static int pw_bwdd_sel(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem
 int launch_pw_bwd_data(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int cit = op.Cin > 8 ? 16 : 8;
   const int Cout4 = (op.Cout + 3) & ~3;
-  const size_t smem = sizeof(PwChan) * cit + sizeof(PwOut) * Cout4 + sizeof(float) * ((size_t)Cout4 * cit + 4 * 2 * cit);
+  const size_t smem = sizeof(PwChan) * cit + sizeof(PwOut) * Cout4 + sizeof(float) * ((size_t)Cout4 * cit + 4 * 2 * cit + 4 * 2 * cit * 32);
   const long long nq = (long long)op.N * (op.L_out >> 2);
   const int ty = (op.Cin + cit - 1) / cit;
   const int G = pick_G(nq, ty, sm_count);
