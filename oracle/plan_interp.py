@@ -25,23 +25,30 @@ from seist_b200.plan import ACT_GELU, OUT_SIGMOID, OUT_SOFTMAX, Op, Plan, View
 M64 = (1 << 64) - 1
 
 
-def rng_u32(step_seed: int, stream: int, idx: np.ndarray) -> np.ndarray:
-    """Counter-based generator shared with csrc/common.cuh::rng_u32 (splitmix64 finaliser)."""
+def rng_u64(step_seed: int, stream: int, qidx: np.ndarray) -> np.ndarray:
+    """Counter-based generator shared with csrc/common.cuh::rng_u64 (splitmix64 finaliser of the QUAD index)."""
     with np.errstate(over="ignore"):
         z = np.uint64((step_seed * 0xD1342543DE82EF95 + ((stream << 32) | 0x9E3779B9)) & M64)
-        z = z + idx.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        z = z + qidx.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
         z ^= z >> np.uint64(30)
         z *= np.uint64(0xBF58476D1CE4E5B9)
         z ^= z >> np.uint64(27)
         z *= np.uint64(0x94D049BB133111EB)
         z ^= z >> np.uint64(31)
-    return (z >> np.uint64(32)).astype(np.uint32)
+    return z
+
+
+def rng_u16(step_seed: int, stream: int, idx: np.ndarray) -> np.ndarray:
+    """16-bit lane (idx & 3) of the hash of quad (idx >> 2) - csrc/common.cuh::keep_scale."""
+    idx = idx.astype(np.uint64)
+    h = rng_u64(step_seed, stream, idx >> np.uint64(2))
+    return ((h >> (np.uint64(16) * (idx & np.uint64(3)))) & np.uint64(0xFFFF)).astype(np.uint32)
 
 
 def keep_mask(p: float, step_seed: int, stream: int, idx: np.ndarray) -> torch.Tensor:
-    """1/(1-p) where kept, 0 where dropped."""
-    thr = np.uint32(min(np.float32(p) * np.float32(4294967296.0), np.float32(4294967040.0)))
-    keep = rng_u32(step_seed, stream, idx) >= thr
+    """1/(1-p) where kept, 0 where dropped (drop probability quantised to 2^-16 like the CUDA side)."""
+    thr = np.uint32(min(np.rint(np.float32(p) * np.float32(65536.0)), np.float32(65535.0)))
+    keep = rng_u16(step_seed, stream, idx) >= thr
     return torch.from_numpy(keep.astype(np.float32)) / np.float32(1.0 - np.float32(p))
 
 

@@ -225,10 +225,11 @@ __global__ void __launch_bounds__(BT_NT) bww_tc_kernel(const __grid_constant__ S
         const int lq = l0 + 4 * q;
         if (op.p_elem > 0.f && lq < L) {
           const uint64_t e = ((uint64_t)n * Cout + row) * (uint64_t)L + lq;
-          g.x *= keep_scale(op.p_elem, seed, op.seed_elem, e);
-          g.y *= keep_scale(op.p_elem, seed, op.seed_elem, e + 1);
-          g.z *= keep_scale(op.p_elem, seed, op.seed_elem, e + 2);
-          g.w *= keep_scale(op.p_elem, seed, op.seed_elem, e + 3);
+          const float4 kp = keep4(op.p_elem, seed, op.seed_elem, e);
+          g.x *= kp.x;
+          g.y *= kp.y;
+          g.z *= kp.z;
+          g.w *= kp.w;
         }
         if (lq >= L) g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (blockIdx.y == 0 && op.dbias != nullptr) atomicAdd(&bias_s[row], (g.x + g.y) + (g.z + g.w));

@@ -14,6 +14,10 @@
 // (BN-backward prologue for gacc; BN-apply / GELU / up-sampling / zero padding for the input).  Threads are
 // laid out as TG = TGM*nci tile coordinates x PG sample groups; the sample groups are folded through shared
 // memory at the end, one float atomic per dW element per CTA.
+//
+// FFMA2: the gacc rows are parked in shared memory interleaved in channel pairs ({g[2r][s], g[2r+1][s]}), so a
+// 16-byte load yields two aligned (even, odd channel) register pairs; each FFMA2 multiplies such a pair with one
+// broadcast window sample: 8*K packed FMAs per quad instead of 16*K scalar ones.
 #include "common.cuh"
 #include "conv_common.cuh"
 
@@ -38,14 +42,14 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
   constexpr int RW = (K + 1) | 1;                      // odd row pitch of the final fold
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int L = op.L_out;
-  const int gpitch = PC + 4;
+  const int gpitch = 2 * PC + 8;                         // pitch of a channel-PAIR row (= 8 mod 32 floats)
   const int gs_in = op.Cin / op.groups, gs_out = op.Cout / op.groups;
   const int tpg = (gs_out + CO_B - 1) / CO_B;            // output-channel tiles per group
   const int grp = blockIdx.y / tpg;
   const int Cin_hi = (grp + 1) * gs_in, Cout_hi = (grp + 1) * gs_out;
   const int width = PC * S + K - S;
-  float* g_s = reinterpret_cast<float*>(sm_raw);          // [CO_B][gpitch]
-  float* in_s = g_s + CO_B * gpitch;                      // [CI_B][pitch]
+  float* g_s = reinterpret_cast<float*>(sm_raw);          // [CO_B/2][gpitch]
+  float* in_s = g_s + (CO_B / 2) * gpitch;                // [CI_B][pitch]
   BkOut* oc_s = reinterpret_cast<BkOut*>(g_s + area_f);   // [CO_B]
   float* src_s = reinterpret_cast<float*>(oc_s + CO_B);   // [CI_B][width+4] (up-sampled input only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -76,14 +80,14 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
   const bool active = pg < PG;
   const int tm = tcoord / nci, tn = tcoord - tm * nci;
   const float* my_in = in_s + tn * pitch;
-  const float* my_g = g_s + tm * gpitch;
+  const float* my_g = g_s + tm * gpitch;                  // pair rows tm and tm + TGM: channels 2*(tm + TGM*ip) + {0,1}
 
-  float acc[4][K];
-  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+  float2 acc[2][K];                                       // [pair row ip][tap]: .x even channel, .y odd channel
+  float2 bacc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int t = 0; t < K; ++t) acc[i][t] = 0.f;
+    for (int t = 0; t < K; ++t) acc[i][t] = make_float2(0.f, 0.f);
 
   const int chunks_per_n = (L + PC - 1) / PC;
   const int total = op.N * chunks_per_n;
@@ -92,44 +96,53 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
     const int n = tile / chunks_per_n;
     const int l0 = (tile - n * chunks_per_n) * PC;
     const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
-    // ---- gacc rows ------------------------------------------------------------------------------
-    for (int idx = tid; idx < CO_B * QPR; idx += BK_NT) {
-      const int row = idx / QPR, q = idx - row * QPR;
-      const int co = co_base + row, l = l0 + 4 * q;
-      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (co < Cout_hi && l < L) {
-        const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l;
-        if (op.out_dxd) gv = bk_ldg4(op.out_dxd + off);
-        if (need_x) {
-          const float4 x = bk_ldg4(op.out.x + off);
-          if (has_bn) {
-            const float4 du = bk_ldg4(op.out.g + off);
-            const BkOut o = oc_s[row];
-            gv.x += fmaf(o.A, du.x, fmaf(o.Bx, x.x, o.Cc));
-            gv.y += fmaf(o.A, du.y, fmaf(o.Bx, x.y, o.Cc));
-            gv.z += fmaf(o.A, du.z, fmaf(o.Bx, x.z, o.Cc));
-            gv.w += fmaf(o.A, du.w, fmaf(o.Bx, x.w, o.Cc));
+    // ---- gacc rows, interleaved in channel pairs: g_s[pr][2*s + half] ---------------------------------
+    for (int idx = tid; idx < (CO_B / 2) * QPR; idx += BK_NT) {
+      const int pr = idx / QPR, q = idx - pr * QPR;
+      const int l = l0 + 4 * q;
+      float4 gh[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = 2 * pr + h, co = co_base + row;
+        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (co < Cout_hi && l < L) {
+          const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l;
+          if (op.out_dxd) gv = bk_ldg4(op.out_dxd + off);
+          if (need_x) {
+            const float4 x = bk_ldg4(op.out.x + off);
+            if (has_bn) {
+              const float4 du = bk_ldg4(op.out.g + off);
+              const BkOut o = oc_s[row];
+              gv.x += fmaf(o.A, du.x, fmaf(o.Bx, x.x, o.Cc));
+              gv.y += fmaf(o.A, du.y, fmaf(o.Bx, x.y, o.Cc));
+              gv.z += fmaf(o.A, du.z, fmaf(o.Bx, x.z, o.Cc));
+              gv.w += fmaf(o.A, du.w, fmaf(o.Bx, x.w, o.Cc));
+            }
+            if (op.out_act == SEIST_OUT_SIGMOID) {
+              gv.x *= x.x * (1.f - x.x);
+              gv.y *= x.y * (1.f - x.y);
+              gv.z *= x.z * (1.f - x.z);
+              gv.w *= x.w * (1.f - x.w);
+            }
           }
-          if (op.out_act == SEIST_OUT_SIGMOID) {
-            gv.x *= x.x * (1.f - x.x);
-            gv.y *= x.y * (1.f - x.y);
-            gv.z *= x.z * (1.f - x.z);
-            gv.w *= x.w * (1.f - x.w);
+          gv.x *= pf;
+          gv.y *= pf;
+          gv.z *= pf;
+          gv.w *= pf;
+          if (op.p_elem > 0.f) {
+            const uint64_t e = ((uint64_t)n * op.Cout + co) * (uint64_t)L + l;
+            const float4 kp = keep4(op.p_elem, seed, op.seed_elem, e);
+            gv.x *= kp.x;
+            gv.y *= kp.y;
+            gv.z *= kp.z;
+            gv.w *= kp.w;
           }
         }
-        gv.x *= pf;
-        gv.y *= pf;
-        gv.z *= pf;
-        gv.w *= pf;
-        if (op.p_elem > 0.f) {
-          const uint64_t e = ((uint64_t)n * op.Cout + co) * (uint64_t)L + l;
-          gv.x *= keep_scale(op.p_elem, seed, op.seed_elem, e);
-          gv.y *= keep_scale(op.p_elem, seed, op.seed_elem, e + 1);
-          gv.z *= keep_scale(op.p_elem, seed, op.seed_elem, e + 2);
-          gv.w *= keep_scale(op.p_elem, seed, op.seed_elem, e + 3);
-        }
+        gh[h] = gv;
       }
-      bk_st4(g_s + row * gpitch + 4 * q, gv);
+      float* gp = g_s + pr * gpitch + 8 * q;
+      bk_st4(gp, make_float4(gh[0].x, gh[1].x, gh[0].y, gh[1].y));
+      bk_st4(gp + 4, make_float4(gh[0].z, gh[1].z, gh[0].w, gh[1].w));
     }
     // ---- conv-input rows: in_s[r][pos] <-> conv-input coordinate p_base + pos ----------------------
     const int p_base = l0 * S - op.pad_left;
@@ -172,24 +185,33 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
           w[4 * j + 2] = t4.z;
           w[4 * j + 3] = t4.w;
         }
-        float4 gq[4];
+        float2 gp[2][4];                                  // [pair row][sample]
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gq[i] = bk_ld4(my_g + TGM * i * gpitch + 4 * q);
+        for (int i = 0; i < 2; ++i) {
+          const float4 a = bk_ld4(my_g + TGM * i * gpitch + 8 * q), b = bk_ld4(my_g + TGM * i * gpitch + 8 * q + 4);
+          gp[i][0] = make_float2(a.x, a.y);
+          gp[i][1] = make_float2(a.z, a.w);
+          gp[i][2] = make_float2(b.x, b.y);
+          gp[i][3] = make_float2(b.z, b.w);
+        }
 #pragma unroll
         for (int t = 0; t < K; ++t) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float a = acc[i][t];
-            a = fmaf(gq[i].x, w[t], a);
-            a = fmaf(gq[i].y, w[S + t], a);
-            a = fmaf(gq[i].z, w[2 * S + t], a);
-            a = fmaf(gq[i].w, w[3 * S + t], a);
+          for (int i = 0; i < 2; ++i) {
+            float2 a = acc[i][t];
+            a = fma2(gp[i][0], dup2(w[t]), a);
+            a = fma2(gp[i][1], dup2(w[S + t]), a);
+            a = fma2(gp[i][2], dup2(w[2 * S + t]), a);
+            a = fma2(gp[i][3], dup2(w[3 * S + t]), a);
             acc[i][t] = a;
           }
         }
         if (tn == 0) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) bacc[i] += (gq[i].x + gq[i].y) + (gq[i].z + gq[i].w);
+          for (int i = 0; i < 2; ++i) {
+            bacc[i].x += (gp[i][0].x + gp[i][1].x) + (gp[i][2].x + gp[i][3].x);
+            bacc[i].y += (gp[i][0].y + gp[i][1].y) + (gp[i][2].y + gp[i][3].y);
+          }
         }
       }
     }
@@ -200,18 +222,18 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
   float* red = g_s;
   const int R = gs_in * K;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 4; ++i) {                           // round i: pair row ip = i >> 1, half = i & 1
     float* mine = red + (size_t)tid * RW;
 #pragma unroll
-    for (int t = 0; t < K; ++t) mine[t] = acc[i][t];
-    mine[K] = bacc[i];
+    for (int t = 0; t < K; ++t) mine[t] = (i & 1) ? acc[i >> 1][t].y : acc[i >> 1][t].x;
+    mine[K] = (i & 1) ? bacc[i >> 1].y : bacc[i >> 1].x;
     __syncthreads();
     for (int idx = tid; idx < TG * (K + 1); idx += BK_NT) {
       const int tc = idx / (K + 1), e = idx - tc * (K + 1);
       float s = 0.f;
       for (int p = 0; p < PG; ++p) s += red[((size_t)p * TG + tc) * RW + e];
       const int m = tc / nci, cr = tc - m * nci;
-      const int co = co_base + m + TGM * i;
+      const int co = co_base + 2 * (m + TGM * (i >> 1)) + (i & 1);
       if (co < Cout_hi) {
         if (e < K) {
           atomicAdd(&op.dW[(size_t)co * R + (size_t)(ci_lo - grp * gs_in + cr) * K + e], s);
@@ -242,7 +264,7 @@ static int launch_bwwk_t(const SeistOp& op, cudaStream_t s, int sm_count) {
   int pitch = (4 * (PC / 4 - 1) * S + 4 * WQ + 3) & ~3;
   if (pitch < ((width + 3) & ~3)) pitch = (width + 3) & ~3;
   while ((pitch & 31) != 4) pitch += 4;
-  int area_f = CO_B * (PC + 4) + CI_B * pitch;
+  int area_f = (CO_B / 2) * (2 * PC + 8) + CI_B * pitch;
   if (area_f < BK_NT * RW) area_f = BK_NT * RW;
   area_f = (area_f + 3) & ~3;
   const size_t smem = sizeof(float) * (size_t)area_f + sizeof(BkOut) * CO_B +

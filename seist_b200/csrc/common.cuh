@@ -16,6 +16,11 @@ int check_launch(const char* what);
 void set_error(const char* msg);
 
 // ---- math -------------------------------------------------------------------------------------
+// packed fp32 FMA (sm_100 FFMA2, fma.rn.f32x2): two IEEE fused multiply-adds per issue slot, bit-identical to
+// two scalar fmaf.  Measured on B200 (tools/ffma2_probe.cu): 65.7 TFLOP/s vs 46.7 for scalar FFMA.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+
 __device__ __forceinline__ float gelu_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
@@ -32,23 +37,36 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// ---- counter-based RNG (mirrored by oracle/plan_interp.py::rng_u32) ---------------------------
-__device__ __forceinline__ uint32_t rng_u32(uint64_t step_seed, uint32_t stream, uint64_t idx) {
+// ---- counter-based RNG (mirrored by oracle/plan_interp.py::rng_u64 / keep_mask) -----------------
+// One splitmix64 finaliser per QUAD of consecutive element indices; element idx uses the 16-bit lane
+// (idx & 3) of the hash of (idx >> 2).  A keep decision compares the lane with round(p * 65536): the drop
+// probability is quantised to 2^-16 (p = 0.2 -> 0.2000122), the survivors are scaled by the exact 1/(1-p)
+// like torch dropout.  Vector code paths draw four decisions from one hash (keep4).
+__device__ __forceinline__ uint64_t rng_u64(uint64_t step_seed, uint32_t stream, uint64_t qidx) {
   uint64_t z = step_seed * 0xD1342543DE82EF95ull + (((uint64_t)stream << 32) | 0x9E3779B9ull);
-  z += idx * 0x9E3779B97F4A7C15ull;
+  z += qidx * 0x9E3779B97F4A7C15ull;
   z ^= z >> 30;
   z *= 0xBF58476D1CE4E5B9ull;
   z ^= z >> 27;
   z *= 0x94D049BB133111EBull;
   z ^= z >> 31;
-  return (uint32_t)(z >> 32);
+  return z;
 }
 __device__ __forceinline__ uint32_t drop_threshold(float p) {
-  return (uint32_t)fminf(p * 4294967296.0f, 4294967040.0f);
+  return (uint32_t)fminf(rintf(p * 65536.0f), 65535.0f);
 }
-// 1/(1-p) if kept else 0
+// multiplier of the survivors, 0 for dropped elements
 __device__ __forceinline__ float keep_scale(float p, uint64_t seed, uint32_t stream, uint64_t idx) {
-  return rng_u32(seed, stream, idx) >= drop_threshold(p) ? 1.0f / (1.0f - p) : 0.0f;
+  const uint32_t lane = (uint32_t)(rng_u64(seed, stream, idx >> 2) >> (16 * (int)(idx & 3))) & 0xFFFFu;
+  return lane >= drop_threshold(p) ? 1.0f / (1.0f - p) : 0.0f;
+}
+// four consecutive elements idx .. idx+3, idx a multiple of 4: one hash
+__device__ __forceinline__ float4 keep4(float p, uint64_t seed, uint32_t stream, uint64_t idx) {
+  const uint64_t h = rng_u64(seed, stream, idx >> 2);
+  const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32), thr = drop_threshold(p);
+  const float s = 1.0f / (1.0f - p);
+  return make_float4((lo & 0xFFFFu) >= thr ? s : 0.f, (lo >> 16) >= thr ? s : 0.f, (hi & 0xFFFFu) >= thr ? s : 0.f,
+                     (hi >> 16) >= thr ? s : 0.f);
 }
 __device__ __forceinline__ uint64_t load_seed(const uint64_t* p) { return p ? *p : 0ull; }
 

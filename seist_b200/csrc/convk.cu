@@ -26,8 +26,11 @@ struct CkWin {
 };
 
 // acc[c][j] += sum_t w[t][c] * win[j*S + t] for one reduction channel
+// channel pairs ride the two lanes of FFMA2; ck_acc reads channel c, sample j of a [4][4] pair tile
+__device__ __forceinline__ float ck_acc(const float2 (&acc)[4][4], int c, int j) { return (c & 1) ? acc[c >> 1][j].y : acc[c >> 1][j].x; }
+
 template <int K, int S>
-__device__ __forceinline__ void ck_accumulate(const float* irow, const float* wrow, int wstride, float (&acc)[8][4]) {
+__device__ __forceinline__ void ck_accumulate(const float* irow, const float* wrow, int wstride, float2 (&acc)[4][4]) {
   constexpr int NV = CkWin<K, S>::NV;
   float win[NV * 4];
 #pragma unroll
@@ -41,12 +44,12 @@ __device__ __forceinline__ void ck_accumulate(const float* irow, const float* wr
 #pragma unroll
   for (int t = 0; t < K; ++t) {
     const float4 w0 = lds4(wrow + t * wstride), w1 = lds4(wrow + t * wstride + 4);
-    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float2 w[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float v = win[j * S + t];
+      const float2 v = dup2(win[j * S + t]);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[c][j] = fmaf(w[c], v, acc[c][j]);
+      for (int c = 0; c < 4; ++c) acc[c][j] = fma2(w[c], v, acc[c][j]);
     }
   }
 }
@@ -112,11 +115,11 @@ __global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant_
   const float ratio = op.up_src_L > 0 ? (float)Lsrc / (float)op.L_in : 1.f;
   const int p_base = l0 * S - op.pad_left;
 
-  float acc[8][4];
+  float2 acc[4][4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[c][j] = make_float2(0.f, 0.f);
 
   for (int ci0 = 0; ci0 < gs_in; ci0 += CK_CIC) {
     const int cic = min(CK_CIC, gs_in - ci0);
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant_
         const int l = lq + j;
         float v = 0.f;
         if (l < op.L_out) {
-          v = (acc[c][j] + b) * pf * elem_factor(op, seed, n, co, l);
+          v = (ck_acc(acc, c, j) + b) * pf * elem_factor(op, seed, n, co, l);
           if (ra) v += fmaf(asc, ra[l], ash);
           v *= af;
           if (rb) v += fmaf(bsc, rb[l], bsh);
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant_
 //     consecutive input samples per channel.
 // ================================================================================================
 template <int K, int S>
-__global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_constant__ SeistOp op, const int WC) {
+__global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_constant__ SeistOp op, const int WC) {
   extern __shared__ __align__(16) float ck_smem[];
   constexpr int KE = S == 2 ? (K + 1) / 2 : K;          // taps of the stride-1 engine
   constexpr int CPW = S == 2 ? 4 : 8;                   // real input channels per warp
@@ -243,11 +246,11 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
   const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
   const int m_base = p0 + op.pad_left / S - (KE - 1);  // output-sample coordinate of z_s[.][0]
 
-  float acc[8][4];
+  float2 acc[4][4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[c][j] = make_float2(0.f, 0.f);
 
   for (int co0 = 0; co0 < gs_out; co0 += CK_CIC) {
     const int coc = min(CK_CIC, gs_out - co0);
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(CK_NT) convk_bwd_data_kernel(const __grid_cons
         for (int j = 0; j < 4; ++j) {
           const int p = S == 2 ? 2 * (pq + j) + (c & 1) : pq + j;
           if (p >= op.L_in) continue;
-          const float d = acc[c][j];
+          const float d = ck_acc(acc, c, j);
           if (op.up_src_L > 0) {
             int i0, i1;
             float lam;

@@ -94,8 +94,7 @@ __device__ __noinline__ float4 pw_gelu_grad4(float4 u) {
   return u;
 }
 __device__ __noinline__ float4 pw_keep4(float p, uint64_t seed, uint32_t stream, uint64_t idx) {
-  return make_float4(keep_scale(p, seed, stream, idx), keep_scale(p, seed, stream, idx + 1),
-                     keep_scale(p, seed, stream, idx + 2), keep_scale(p, seed, stream, idx + 3));
+  return keep4(p, seed, stream, idx);
 }
 
 // compile-time specialisation keeps the bodies small (instruction cache) and the inner loops free of
@@ -157,9 +156,11 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
     const bool ok = f < NQ;
     const int n = ok ? (int)(f / LQ) : 0;
     const int l = ok ? (int)(f - (long long)n * LQ) * 4 : 0;
-    float4 acc[COUT_T];
+    float2 acc[COUT_T / 2][4];   // [channel pair][sample]: .x = even channel, .y = odd channel (FFMA2 lanes)
 #pragma unroll
-    for (int c = 0; c < COUT_T; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < COUT_T / 2; ++c)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[c][q] = make_float2(0.f, 0.f);
     for (int ci0 = 0; ci0 < Cin8; ci0 += 8) {
       float4 v[8];
 #pragma unroll
@@ -172,14 +173,15 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
         const PwChan& c = ch_s[ci0 + j];
         float4 u = apply_view(v[j], c.sc, c.sh, 0);
         if (F_GELU && c.act == SEIST_ACT_GELU) u = pw_gelu4(u);
-        const float* wr = w_s + (ci0 + j) * COUT_T;
+        const float2* wr = reinterpret_cast<const float2*>(w_s + (ci0 + j) * COUT_T);
+        const float2 ux = dup2(u.x), uy = dup2(u.y), uz = dup2(u.z), uw = dup2(u.w);
 #pragma unroll
-        for (int co = 0; co < COUT_T; ++co) {
-          const float w = wr[co];
-          acc[co].x = fmaf(w, u.x, acc[co].x);
-          acc[co].y = fmaf(w, u.y, acc[co].y);
-          acc[co].z = fmaf(w, u.z, acc[co].z);
-          acc[co].w = fmaf(w, u.w, acc[co].w);
+        for (int cp = 0; cp < COUT_T / 2; ++cp) {
+          const float2 w = wr[cp];
+          acc[cp][0] = fma2(w, ux, acc[cp][0]);
+          acc[cp][1] = fma2(w, uy, acc[cp][1]);
+          acc[cp][2] = fma2(w, uz, acc[cp][2]);
+          acc[cp][3] = fma2(w, uw, acc[cp][3]);
         }
       }
     }
@@ -189,7 +191,8 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
     for (int col = 0; col < COUT_T; ++col) {
       const int co = co_base + col;
       if (co >= op.Cout) break;
-      float4 r = acc[col];
+      const float2(&ap)[4] = acc[col >> 1];
+      float4 r = (col & 1) ? make_float4(ap[0].y, ap[1].y, ap[2].y, ap[3].y) : make_float4(ap[0].x, ap[1].x, ap[2].x, ap[3].x);
       const float b = ep_s[col];
       r.x = (r.x + b) * pf;
       r.y = (r.y + b) * pf;
@@ -310,9 +313,11 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
     const int n = ok ? (int)(f / LQ) : 0;
     const int l = ok ? (int)(f - (long long)n * LQ) * 4 : 0;
     const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
-    float4 acc[CI_T];
+    float2 acc[CI_T / 2][4];   // [target-channel pair][sample] (FFMA2 lanes = even / odd channel)
 #pragma unroll
-    for (int c = 0; c < CI_T; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < CI_T / 2; ++c)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[c][q] = make_float2(0.f, 0.f);
     const size_t obase = ((size_t)n * op.out.Ct + op.out.c0) * (size_t)L + l;
     for (int co0 = 0; co0 < Cout4; co0 += PW_BD_CG) {
       float4 dx[PW_BD_CG], du[PW_BD_CG], xo[PW_BD_CG];
@@ -350,14 +355,15 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
           gv.z *= kp.z;
           gv.w *= kp.w;
         }
-        const float* wr = w_s + co * CI_T;   // zero rows for co >= Cout
+        const float2* wr = reinterpret_cast<const float2*>(w_s + co * CI_T);   // zero rows for co >= Cout
+        const float2 gx = dup2(gv.x), gy = dup2(gv.y), gz = dup2(gv.z), gw = dup2(gv.w);
 #pragma unroll
-        for (int c = 0; c < CI_T; ++c) {
-          const float w = wr[c];
-          acc[c].x = fmaf(w, gv.x, acc[c].x);
-          acc[c].y = fmaf(w, gv.y, acc[c].y);
-          acc[c].z = fmaf(w, gv.z, acc[c].z);
-          acc[c].w = fmaf(w, gv.w, acc[c].w);
+        for (int cp = 0; cp < CI_T / 2; ++cp) {
+          const float2 w = wr[cp];
+          acc[cp][0] = fma2(w, gx, acc[cp][0]);
+          acc[cp][1] = fma2(w, gy, acc[cp][1]);
+          acc[cp][2] = fma2(w, gz, acc[cp][2]);
+          acc[cp][3] = fma2(w, gw, acc[cp][3]);
         }
       }
     }
@@ -366,7 +372,8 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
     for (int col = 0; col < CI_T; ++col) {
       const PwChan& c = ch_s[col];
       if (c.g == nullptr) continue;
-      float4 gg = acc[col];
+      const float2(&ap)[4] = acc[col >> 1];
+      float4 gg = (col & 1) ? make_float4(ap[0].y, ap[1].y, ap[2].y, ap[3].y) : make_float4(ap[0].x, ap[1].x, ap[2].x, ap[3].x);
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       const long long off = (long long)n * c.nstride + l;
       if ((F_GELU && c.act == SEIST_ACT_GELU) || c.bn >= 0) x = ldg4(c.x + off);
@@ -613,7 +620,8 @@ constexpr int BW_NT = 256;
 // BW_PC = output samples per chunk (128, or 512 for narrow tiles where the per-chunk barriers/latency dominate)
 template <int CO_B, int R_B, bool K1, int BW_PC>
 __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ SeistOp op, const int nci_max) {
-  constexpr int BW_PITCH = BW_PC + 4;   // gacc row pitch (floats), keeps 16-byte alignment
+  constexpr int BW_PITCH = BW_PC + 4;   // input row pitch (floats), keeps 16-byte alignment
+  constexpr int BW_GP = 2 * BW_PC + 8;  // gacc channel-PAIR row pitch: g_s[pr][2*s + half] (FFMA2 operand pairs)
   extern __shared__ __align__(16) unsigned char sm_raw[];
   constexpr int TGM = CO_B / 4, TGN = R_B / 8, TG = TGM * TGN, PG = BW_NT / TG;
   static_assert(TG <= BW_NT && BW_NT % TG == 0, "bad tile");
@@ -626,10 +634,10 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
   const int R = gs_in * k;
   const int width = BW_PC * S + k - S;
   const int pitch = K1 ? BW_PITCH : (width | 1);            // odd pitch: scalar reads spread over banks
-  const int stage_f = CO_B * BW_PITCH + nci_max * pitch;
+  const int stage_f = (CO_B / 2) * BW_GP + nci_max * pitch;
   const int area_f = stage_f > BW_NT * 36 ? stage_f : BW_NT * 36;
-  float* g_s = reinterpret_cast<float*>(sm_raw);            // [CO_B][BW_PITCH]
-  float* in_s = g_s + CO_B * BW_PITCH;                      // [nci][pitch]
+  float* g_s = reinterpret_cast<float*>(sm_raw);            // [CO_B/2][BW_GP]
+  float* in_s = g_s + (CO_B / 2) * BW_GP;                   // [nci][pitch]
   PwOut* oc_s = reinterpret_cast<PwOut*>(g_s + ((area_f + 3) & ~3));   // [CO_B]
   PwChan* ch_s = reinterpret_cast<PwChan*>(oc_s + CO_B);                // [nci_max] (k = 1 fast path)
   float* src_s = reinterpret_cast<float*>(ch_s + nci_max + 1);          // [nci_max][width+4] (up-sampled input only)
@@ -671,12 +679,12 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
     const int q = rr / k, t = rr - q * k;               // q: input channel inside the group
     roff[j] = (grp * gs_in + q - ci_lo) * pitch + t;
   }
-  float acc[4][8];
-  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+  float2 acc[2][8];   // [pair row ip][column]: channels 2*(tm + TGM*ip) + {0 (.x), 1 (.y)}
+  float2 bacc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
   const int chunks_per_n = (L + BW_PC - 1) / BW_PC;
   const int total = op.N * chunks_per_n;
@@ -687,43 +695,52 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
     const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
     // ---- gacc rows ------------------------------------------------------------------------------
     if (vec) {
-      for (int idx = tid; idx < CO_B * QPR; idx += BW_NT) {
-        const int row = idx / QPR, q = idx - row * QPR;
-        const int co = co_base + row, l = l0 + 4 * q;
-        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (co < Cout && l < L) {
-          const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l;
-          if (op.out_dxd) gv = ldg4(op.out_dxd + off);
-          if (need_x) {
-            const float4 x = ldg4(op.out.x + off);
-            if (has_bn) {
-              const float4 du = ldg4(op.out.g + off);
-              const PwOut o = oc_s[row];
-              gv.x += fmaf(o.A, du.x, fmaf(o.Bx, x.x, o.Cc));
-              gv.y += fmaf(o.A, du.y, fmaf(o.Bx, x.y, o.Cc));
-              gv.z += fmaf(o.A, du.z, fmaf(o.Bx, x.z, o.Cc));
-              gv.w += fmaf(o.A, du.w, fmaf(o.Bx, x.w, o.Cc));
+      for (int idx = tid; idx < (CO_B / 2) * QPR; idx += BW_NT) {
+        const int pr = idx / QPR, q = idx - pr * QPR;
+        const int l = l0 + 4 * q;
+        float4 gh[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = 2 * pr + h, co = co_base + row;
+          float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (co < Cout && l < L) {
+            const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l;
+            if (op.out_dxd) gv = ldg4(op.out_dxd + off);
+            if (need_x) {
+              const float4 x = ldg4(op.out.x + off);
+              if (has_bn) {
+                const float4 du = ldg4(op.out.g + off);
+                const PwOut o = oc_s[row];
+                gv.x += fmaf(o.A, du.x, fmaf(o.Bx, x.x, o.Cc));
+                gv.y += fmaf(o.A, du.y, fmaf(o.Bx, x.y, o.Cc));
+                gv.z += fmaf(o.A, du.z, fmaf(o.Bx, x.z, o.Cc));
+                gv.w += fmaf(o.A, du.w, fmaf(o.Bx, x.w, o.Cc));
+              }
+              if (op.out_act == SEIST_OUT_SIGMOID) {
+                gv.x *= x.x * (1.f - x.x);
+                gv.y *= x.y * (1.f - x.y);
+                gv.z *= x.z * (1.f - x.z);
+                gv.w *= x.w * (1.f - x.w);
+              }
             }
-            if (op.out_act == SEIST_OUT_SIGMOID) {
-              gv.x *= x.x * (1.f - x.x);
-              gv.y *= x.y * (1.f - x.y);
-              gv.z *= x.z * (1.f - x.z);
-              gv.w *= x.w * (1.f - x.w);
+            gv.x *= pf;
+            gv.y *= pf;
+            gv.z *= pf;
+            gv.w *= pf;
+            if (op.p_elem > 0.f) {
+              const uint64_t e = ((uint64_t)n * Cout + co) * (uint64_t)L + l;
+              const float4 kp = keep4(op.p_elem, seed, op.seed_elem, e);
+              gv.x *= kp.x;
+              gv.y *= kp.y;
+              gv.z *= kp.z;
+              gv.w *= kp.w;
             }
           }
-          gv.x *= pf;
-          gv.y *= pf;
-          gv.z *= pf;
-          gv.w *= pf;
-          if (op.p_elem > 0.f) {
-            const uint64_t e = ((uint64_t)n * Cout + co) * (uint64_t)L + l;
-            gv.x *= keep_scale(op.p_elem, seed, op.seed_elem, e);
-            gv.y *= keep_scale(op.p_elem, seed, op.seed_elem, e + 1);
-            gv.z *= keep_scale(op.p_elem, seed, op.seed_elem, e + 2);
-            gv.w *= keep_scale(op.p_elem, seed, op.seed_elem, e + 3);
-          }
+          gh[h] = gv;
         }
-        st4(g_s + row * BW_PITCH + 4 * q, gv);
+        float* gp = g_s + pr * BW_GP + 8 * q;
+        st4(gp, make_float4(gh[0].x, gh[1].x, gh[0].y, gh[1].y));
+        st4(gp + 4, make_float4(gh[0].z, gh[1].z, gh[0].w, gh[1].w));
       }
     } else {
       for (int idx = tid; idx < CO_B * BW_PC; idx += BW_NT) {
@@ -737,7 +754,7 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
           kc.Cc = oc_s[row].Cc;
           v = out_grad_at(op, kc, n, co, l) * pf * elem_factor(op, seed, n, co, l);
         }
-        g_s[row * BW_PITCH + pos] = v;
+        g_s[(row >> 1) * BW_GP + 2 * pos + (row & 1)] = v;
       }
     }
     // ---- conv-input rows --------------------------------------------------------------------------
@@ -786,9 +803,16 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
     __syncthreads();
     // ---- accumulate ---------------------------------------------------------------------------------
     for (int q = pg; q < QPR; q += PG) {
-      float4 gq[4];
+      float2 gp[2][4];   // [pair row][sample]
 #pragma unroll
-      for (int i = 0; i < 4; ++i) gq[i] = ld4(g_s + (tm + TGM * i) * BW_PITCH + 4 * q);
+      for (int i = 0; i < 2; ++i) {
+        const float* gr = g_s + (tm + TGM * i) * BW_GP + 8 * q;
+        const float4 a = ld4(gr), b = ld4(gr + 4);
+        gp[i][0] = make_float2(a.x, a.y);
+        gp[i][1] = make_float2(a.z, a.w);
+        gp[i][2] = make_float2(b.x, b.y);
+        gp[i][3] = make_float2(b.z, b.w);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 iq;
@@ -799,18 +823,21 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
           iq = make_float4(ip[0], ip[S], ip[2 * S], ip[3 * S]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float a = acc[i][j];
-          a = fmaf(gq[i].x, iq.x, a);
-          a = fmaf(gq[i].y, iq.y, a);
-          a = fmaf(gq[i].z, iq.z, a);
-          a = fmaf(gq[i].w, iq.w, a);
+        for (int i = 0; i < 2; ++i) {
+          float2 a = acc[i][j];
+          a = fma2(gp[i][0], dup2(iq.x), a);
+          a = fma2(gp[i][1], dup2(iq.y), a);
+          a = fma2(gp[i][2], dup2(iq.z), a);
+          a = fma2(gp[i][3], dup2(iq.w), a);
           acc[i][j] = a;
         }
       }
       if (tn == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bacc[i] += (gq[i].x + gq[i].y) + (gq[i].z + gq[i].w);
+        for (int i = 0; i < 2; ++i) {
+          bacc[i].x += (gp[i][0].x + gp[i][1].x) + (gp[i][2].x + gp[i][3].x);
+          bacc[i].y += (gp[i][0].y + gp[i][1].y) + (gp[i][2].y + gp[i][3].y);
+        }
       }
     }
     __syncthreads();
@@ -821,10 +848,10 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
   constexpr int RW = 36;
   float* mine = red + (size_t)tid * RW;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 4; ++i) {   // slot i <-> channel 2*(tm + TGM*(i>>1)) + (i&1)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) mine[i * 8 + j] = acc[i][j];
-    mine[32 + i] = bacc[i];
+    for (int j = 0; j < 8; ++j) mine[i * 8 + j] = (i & 1) ? acc[i >> 1][j].y : acc[i >> 1][j].x;
+    mine[32 + i] = (i & 1) ? bacc[i >> 1].y : bacc[i >> 1].x;
   }
   __syncthreads();
   for (int idx = tid; idx < TG * RW; idx += BW_NT) {
@@ -833,10 +860,12 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
     for (int p = 0; p < PG; ++p) s += red[((size_t)p * TG + tc) * RW + e];
     const int m = tc / TGN, nn = tc % TGN;
     if (e < 32) {
-      const int co = co_base + m + TGM * (e >> 3), r = r_base + nn + TGN * (e & 7);
+      const int i = e >> 3;
+      const int co = co_base + 2 * (m + TGM * (i >> 1)) + (i & 1), r = r_base + nn + TGN * (e & 7);
       if (co < Cout && r < R) atomicAdd(&op.dW[(size_t)co * R + r], s);   // W is [Cout][gs_in][k]: row co, column r
     } else if (nn == 0 && blockIdx.z == 0 && op.dbias != nullptr) {
-      const int co = co_base + m + TGM * (e - 32);
+      const int i = e - 32;
+      const int co = co_base + 2 * (m + TGM * (i >> 1)) + (i & 1);
       if (co < Cout) atomicAdd(&op.dbias[co], s);
     }
   }
@@ -850,7 +879,7 @@ static int launch_bww_pc(const SeistOp& op, cudaStream_t s, int sm_count) {
   if (nci_max > op.Cin / op.groups) nci_max = op.Cin / op.groups;
   const int width = BW_PC * S + k - S;
   const int pitch = K1 ? BW_PITCH : (width | 1);
-  int stage_f = CO_B * BW_PITCH + nci_max * pitch;
+  int stage_f = (CO_B / 2) * (2 * BW_PC + 8) + nci_max * pitch;
   if (stage_f < BW_NT * 36) stage_f = BW_NT * 36;
   const size_t smem = sizeof(float) * (size_t)((stage_f + 3) & ~3) + sizeof(PwOut) * CO_B + sizeof(PwChan) * (nci_max + 1) + 64 +
                       (op.up_src_L > 0 ? sizeof(float) * (size_t)nci_max * (width + 4) : 0);

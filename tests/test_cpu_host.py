@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import seist_ref as R
-from oracle.plan_interp import Interp, rng_u32
+from oracle.plan_interp import Interp, keep_mask, rng_u16
 from seist_b200 import _lib
 from seist_b200 import plan as P
 from seist_b200 import models
@@ -118,8 +118,11 @@ def test_plan_structure_and_sync_points():
 
 def test_rng_reference_values():
     import numpy as np
-    v = rng_u32(7, 3, np.arange(4, dtype=np.uint64))
-    assert v.dtype == np.uint32 and len(set(v.tolist())) == 4
+    v = rng_u16(7, 3, np.arange(8, dtype=np.uint64))
+    assert v.dtype == np.uint32 and int(v.max()) < 65536 and len(set(v.tolist())) >= 7
+    # drop rate of the 16-bit lanes: p = 0.2 over 2^20 draws, scaled survivors keep the mean at ~1
+    m = keep_mask(0.2, 11, 5, np.arange(1 << 20, dtype=np.uint64))
+    assert abs(float((m == 0).float().mean()) - 0.2) < 2e-3 and abs(float(m.mean()) - 1.0) < 3e-3
 
 
 def test_library_exports_every_declared_symbol():

@@ -54,9 +54,13 @@ if "--sass" in sys.argv:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(li), "--launch-count", "1"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
-    h = rows[1]
+    # the source page may hold several kernels: sections start with a "Kernel Name" row followed by a header row
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    sec = rows[starts[0]:(starts[1] if len(starts) > 1 else len(rows))]
+    print("source page of:", sec[0][1])
+    h = sec[1]
     ix2 = {n: i for i, n in enumerate(h)}
-    body = rows[2:]
+    body = [r for r in sec[2:] if len(r) == len(h)]
     ops, samp = Counter(), Counter()
     tot = sum(int(r[ix2["Instructions Executed"]]) for r in body) or 1
     tots = sum(int(r[ix2["# Samples"]]) for r in body) or 1
