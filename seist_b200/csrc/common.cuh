@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include "../../include/seist_b200.h"
 
+#define SEIST_ACT_NONE 0
 #define SEIST_ACT_GELU 1
 #define SEIST_OUT_SIGMOID 1
 #define SEIST_OUT_SOFTMAX 2

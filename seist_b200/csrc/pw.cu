@@ -59,6 +59,32 @@ __device__ __forceinline__ float4 apply_view(float4 v, float sc, float sh, int a
   return v;
 }
 
+// ---- pooled consumer view (reference LAAB / KV aggregation: AvgPool1d(P) + MaxPool1d(P), models/seist.py:62-76) ----
+// the 4 pooled samples l..l+3 of a channel come from the 4*P contiguous source samples starting at l*P
+__device__ __forceinline__ float pool_pair(float a, float b) { return 0.5f * (a + b) + fmaxf(a, b); }
+__device__ __forceinline__ float4 pw_load_pooled(const float* src, int P, float sc, float sh) {
+  float4 r;
+  if (P == 2) {
+    const float4 a = apply_view(ldg4(src), sc, sh, 0), b = apply_view(ldg4(src + 4), sc, sh, 0);
+    r = make_float4(pool_pair(a.x, a.y), pool_pair(a.z, a.w), pool_pair(b.x, b.y), pool_pair(b.z, b.w));
+  } else {
+    const int QP = P >> 2;   // float4 per pooled sample (P = 4, 8)
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float sum = 0.f, mx = -INFINITY;
+      for (int i = 0; i < QP; ++i) {
+        const float4 a = apply_view(ldg4(src + 4 * (j * QP + i)), sc, sh, 0);
+        sum += (a.x + a.y) + (a.z + a.w);
+        mx = fmaxf(fmaxf(mx, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
+      }
+      o[j] = sum / (float)P + mx;
+    }
+    r = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  return r;
+}
+
 // CTA-wide reduction of per-thread partial sums part[NV] -> double atomics.  red_s: [4][NV] floats.
 template <int NV, typename F>
 __device__ __forceinline__ void cta_reduce_atomic(float (&part)[NV], float* red_s, F&& sink) {
@@ -99,7 +125,7 @@ __device__ __noinline__ float4 pw_keep4(float p, uint64_t seed, uint32_t stream,
 
 // compile-time specialisation keeps the bodies small (instruction cache) and the inner loops free of
 // runtime feature tests: F_ELEM element dropout, F_RES residual views, F_GELU some view applies GELU
-template <int COUT_T, bool F_ELEM, bool F_RES, bool F_GELU>
+template <int COUT_T, bool F_ELEM, bool F_RES, bool F_GELU, bool F_POOL = false>
 __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant__ SeistOp op, const int G) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cin = op.Cin, Cin8 = (Cin + 7) & ~7;
@@ -166,12 +192,13 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const PwChan& c = ch_s[ci0 + j];
-        v[j] = ldg4(c.x + (long long)n * c.nstride + l);
+        if (F_POOL) v[j] = pw_load_pooled(c.x + (long long)n * c.nstride + (long long)l * op.pool, op.pool, c.sc, c.sh);
+        else v[j] = ldg4(c.x + (long long)n * c.nstride + l);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const PwChan& c = ch_s[ci0 + j];
-        float4 u = apply_view(v[j], c.sc, c.sh, 0);
+        float4 u = F_POOL ? v[j] : apply_view(v[j], c.sc, c.sh, 0);
         if (F_GELU && c.act == SEIST_ACT_GELU) u = pw_gelu4(u);
         const float2* wr = reinterpret_cast<const float2*>(w_s + (ci0 + j) * COUT_T);
         const float2 ux = dup2(u.x), uy = dup2(u.y), uz = dup2(u.z), uw = dup2(u.w);
@@ -261,7 +288,7 @@ struct PwOut {   // per output channel of the forward op, resolved once per CTA
   float A, Bx, Cc;
 };
 
-template <int CI_T, bool F_ELEM, bool F_GELU>
+template <int CI_T, bool F_ELEM, bool F_GELU, bool F_POOL = false>
 __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cout = op.Cout, Cout4 = (Cout + 3) & ~3, Cin = op.Cin;
@@ -375,6 +402,45 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
       const float2(&ap)[4] = acc[col >> 1];
       float4 gg = (col & 1) ? make_float4(ap[0].y, ap[1].y, ap[2].y, ap[3].y) : make_float4(ap[0].x, ap[1].x, ap[2].x, ap[3].x);
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (F_POOL) {
+        // route the 4 pooled gradients to their 4*P source samples: g * (1/P + [first arg max])
+        const int P = op.pool;
+        const long long soff = (long long)n * c.nstride + (long long)l * P;
+        const float gq[4] = {gg.x, gg.y, gg.z, gg.w};
+        const float invp = 1.f / (float)P;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float* xs = c.x + soff + j * P;
+          float* gs = c.g + soff + j * P;
+          int am = 0;
+          float mx = -INFINITY;
+          for (int i = 0; i < P; ++i) {
+            const float u = fmaf(c.sc, __ldg(xs + i), c.sh);
+            if (u > mx) {
+              mx = u;
+              am = i;
+            }
+          }
+          for (int i = 0; i < P; i += 2) {   // P is even: pairs keep the stores 8-byte wide
+            float2 g2 = make_float2(gq[j] * (invp + (i == am ? 1.f : 0.f)), gq[j] * (invp + (i + 1 == am ? 1.f : 0.f)));
+            const float2 x2 = __ldg(reinterpret_cast<const float2*>(xs + i));
+            s1 += g2.x + g2.y;
+            s2 = fmaf(g2.x, (x2.x - c.mu) * c.istd, fmaf(g2.y, (x2.y - c.mu) * c.istd, s2));
+            if (c.accum) {
+              const float2 old = *reinterpret_cast<const float2*>(gs + i);
+              g2.x += old.x;
+              g2.y += old.y;
+            }
+            *reinterpret_cast<float2*>(gs + i) = g2;
+          }
+        }
+        if (c.bn >= 0) {
+          my_st[(2 * col) * 32] += s1;
+          my_st[(2 * col + 1) * 32] += s2;
+        }
+        continue;
+      }
       const long long off = (long long)n * c.nstride + l;
       if ((F_GELU && c.act == SEIST_ACT_GELU) || c.bn >= 0) x = ldg4(c.x + off);
       if (F_GELU && c.act == SEIST_ACT_GELU) {
@@ -500,9 +566,17 @@ __global__ void __launch_bounds__(PW_NT) res_bwd4_kernel(const __grid_constant__
 // ================================================================================================
 // launchers
 // ================================================================================================
+// pooled input (AvgPool + MaxPool in front of the 1x1 conv): one un-activated view of exactly pool * L_out
+// samples, no dropout / residual in the epilogue (true for every LAAB / KV-aggregation conv of the family)
+static bool pw_pooled_ok(const SeistOp& op) {
+  if (op.pool != 2 && op.pool != 4 && op.pool != 8) return false;
+  if (op.n_in != 1 || op.in[0].act != SEIST_ACT_NONE || op.in[0].L != op.L_out * op.pool) return false;
+  return op.p_elem <= 0.f && op.res_a.C == 0 && op.res_b.C == 0;
+}
 bool pw_eligible(const SeistOp& op) {
-  if (op.k != 1 || op.stride != 1 || op.groups != 1 || op.pool > 1 || op.up_src_L > 0) return false;
+  if (op.k != 1 || op.stride != 1 || op.groups != 1 || op.up_src_L > 0) return false;
   if (op.L_out & 3) return false;
+  if (op.pool > 1) return pw_pooled_ok(op);
   return true;
 }
 
@@ -537,6 +611,11 @@ static int pw_fwd_go(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, 
 }
 template <int COT>
 static int pw_fwd_sel(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
+  if (op.pool > 1) {
+    int rc = pw_set_smem(pw_fwd_kernel<COT, false, false, false, true>, smem);
+    if (!rc) pw_fwd_kernel<COT, false, false, false, true><<<grid, PW_NT, smem, s>>>(op, G);
+    return rc;
+  }
   const int sel = (op.p_elem > 0.f ? 4 : 0) | ((op.res_a.C > 0 || op.res_b.C > 0) ? 2 : 0) | (any_gelu(op) ? 1 : 0);
   switch (sel) {
     case 0: return pw_fwd_go<COT, false, false, false>(op, s, grid, smem, G);
@@ -572,6 +651,11 @@ static int pw_bwdd_go(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem,
 }
 template <int CIT>
 static int pw_bwdd_sel(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
+  if (op.pool > 1) {
+    int rc = pw_set_smem(pw_bwd_data_kernel<CIT, false, false, true>, smem);
+    if (!rc) pw_bwd_data_kernel<CIT, false, false, true><<<grid, PW_NT, smem, s>>>(op, G);
+    return rc;
+  }
   const int sel = (op.p_elem > 0.f ? 2 : 0) | (any_gelu(op) ? 1 : 0);
   switch (sel) {
     case 0: return pw_bwdd_go<CIT, false, false>(op, s, grid, smem, G);
@@ -759,7 +843,19 @@ __global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ Seis
     }
     // ---- conv-input rows --------------------------------------------------------------------------
     const int p_base = l0 * S - op.pad_left;
-    if (K1 && vec && plain) {
+    if (K1 && vec && op.pool > 1 && op.up_src_L == 0 && op.in[0].act == SEIST_ACT_NONE && Lsrc == L * op.pool &&
+        (op.pool == 2 || op.pool == 4 || op.pool == 8)) {
+      for (int idx = tid; idx < nci * QPR; idx += BW_NT) {
+        const int row = idx / QPR, q = idx - row * QPR;
+        const int l = l0 + 4 * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < L) {
+          const PwChan& c = ch_s[row];
+          v = pw_load_pooled(c.x + (long long)n * c.nstride + (long long)l * op.pool, op.pool, c.sc, c.sh);
+        }
+        st4(in_s + row * pitch + 4 * q, v);
+      }
+    } else if (K1 && vec && plain) {
       for (int idx = tid; idx < nci * QPR; idx += BW_NT) {
         const int row = idx / QPR, q = idx - row * QPR;
         const int l = l0 + 4 * q;
