@@ -206,9 +206,14 @@ def main():
     for _ in range(max(args.warmup, 3)):
         trainer.step(x_d, t_d)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    profiling = os.environ.get("SEIST_PROFILE") == "1"     # ncu --profile-from-start off: capture the timed steps only
+    if profiling:
+        torch.cuda.profiler.start()
     t0 = time.time()
     ms = timed(lambda: trainer.step(x_d, t_d), args.steps)
     t1 = time.time()
+    if profiling:
+        torch.cuda.profiler.stop()
     clocks = sampler.summary(t0, t1) if sampler else None
     loss_val = float(trainer.loss_out.item())
     value = args.batch * world * args.steps / (ms / 1e3)
@@ -234,8 +239,18 @@ def main():
         rows.sort(key=lambda r: -r["ms"])
         top = rows[0]
         ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+        # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/dram_traffic.json:
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch at this batch size), null if not captured
+        traffic = None
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+            ent = cap.get("ops", {}).get(top["name"])
+            if ent and cap.get("model") == args.model and cap.get("batch") == args.batch:
+                traffic = ent["dram_bytes"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "ms": top["ms"], "algorithmic_bytes": top["bytes"],
+                    "frac": ach / hbm_peak, "traffic": traffic, "ms": top["ms"], "algorithmic_bytes": top["bytes"],
                     "share_of_step": top["ms"] / tot, "peak_source": peak_src}
         if args.op_times:
             os.makedirs(os.path.dirname(os.path.abspath(args.op_times)), exist_ok=True)

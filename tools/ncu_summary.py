@@ -19,7 +19,7 @@ M = {
 }
 STALLS = ["long_scoreboard", "wait", "short_scoreboard", "barrier", "no_instruction", "not_selected", "dispatch_stall",
           "math_pipe_throttle", "mio_throttle", "lg_throttle", "branch_resolving", "imc_miss"]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
 ix = {h: i for i, h in enumerate(hdr)}
