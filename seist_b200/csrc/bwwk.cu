@@ -34,10 +34,10 @@ struct BkOut {
 };
 }  // namespace
 
-template <int K, int S, int TGM>
+template <int K, int S, int TGM, int NPR>   // NPR pair rows (2*NPR output channels) per thread
 __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ SeistOp op, const int CI_B, const int PC,
                                                         const int pitch, const int area_f) {
-  constexpr int CO_B = 4 * TGM;
+  constexpr int CO_B = 2 * NPR * TGM;
   constexpr int WN = K + 3 * S, WQ = (WN + 3) / 4;
   constexpr int RW = (K + 1) | 1;                      // odd row pitch of the final fold
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -80,14 +80,16 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
   const bool active = pg < PG;
   const int tm = tcoord / nci, tn = tcoord - tm * nci;
   const float* my_in = in_s + tn * pitch;
-  const float* my_g = g_s + tm * gpitch;                  // pair rows tm and tm + TGM: channels 2*(tm + TGM*ip) + {0,1}
+  const float* my_g = g_s + tm * gpitch;                  // pair rows tm + TGM*ip: channels 2*(tm + TGM*ip) + {0,1}
 
-  float2 acc[2][K];                                       // [pair row ip][tap]: .x even channel, .y odd channel
-  float2 bacc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  float2 acc[NPR][K];                                     // [pair row ip][tap]: .x even channel, .y odd channel
+  float2 bacc[NPR];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < NPR; ++i) {
+    bacc[i] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < K; ++t) acc[i][t] = make_float2(0.f, 0.f);
+  }
 
   const int chunks_per_n = (L + PC - 1) / PC;
   const int total = op.N * chunks_per_n;
@@ -185,9 +187,9 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
           w[4 * j + 2] = t4.z;
           w[4 * j + 3] = t4.w;
         }
-        float2 gp[2][4];                                  // [pair row][sample]
+        float2 gp[NPR][4];                                // [pair row][sample]
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NPR; ++i) {
           const float4 a = bk_ld4(my_g + TGM * i * gpitch + 8 * q), b = bk_ld4(my_g + TGM * i * gpitch + 8 * q + 4);
           gp[i][0] = make_float2(a.x, a.y);
           gp[i][1] = make_float2(a.z, a.w);
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
 #pragma unroll
         for (int t = 0; t < K; ++t) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
+          for (int i = 0; i < NPR; ++i) {
             float2 a = acc[i][t];
             a = fma2(gp[i][0], dup2(w[t]), a);
             a = fma2(gp[i][1], dup2(w[S + t]), a);
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
         }
         if (tn == 0) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
+          for (int i = 0; i < NPR; ++i) {
             bacc[i].x += (gp[i][0].x + gp[i][1].x) + (gp[i][2].x + gp[i][3].x);
             bacc[i].y += (gp[i][0].y + gp[i][1].y) + (gp[i][2].y + gp[i][3].y);
           }
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
   float* red = g_s;
   const int R = gs_in * K;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {                           // round i: pair row ip = i >> 1, half = i & 1
+  for (int i = 0; i < 2 * NPR; ++i) {                     // round i: pair row ip = i >> 1, half = i & 1
     float* mine = red + (size_t)tid * RW;
 #pragma unroll
     for (int t = 0; t < K; ++t) mine[t] = (i & 1) ? acc[i >> 1][t].y : acc[i >> 1][t].x;
@@ -246,9 +248,9 @@ __global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ 
   }
 }
 
-template <int K, int S, int TGM>
+template <int K, int S, int TGM, int NPR>
 static int launch_bwwk_t(const SeistOp& op, cudaStream_t s, int sm_count) {
-  constexpr int CO_B = 4 * TGM;
+  constexpr int CO_B = 2 * NPR * TGM;
   constexpr int WQ = (K + 3 * S + 3) / 4;
   constexpr int RW = (K + 1) | 1;
   const int gs_in = op.Cin / op.groups, gs_out = op.Cout / op.groups;
@@ -275,18 +277,23 @@ static int launch_bwwk_t(const SeistOp& op, cudaStream_t s, int sm_count) {
   if (gx > tiles) gx = tiles;
   if (gx < 1) gx = 1;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(bwwk_kernel<K, S, TGM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(bwwk_kernel<K, S, TGM, NPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  bwwk_kernel<K, S, TGM><<<dim3((unsigned)gx, gy, gz), BK_NT, smem, s>>>(op, CI_B, PC, pitch, area_f);
+  bwwk_kernel<K, S, TGM, NPR><<<dim3((unsigned)gx, gy, gz), BK_NT, smem, s>>>(op, CI_B, PC, pitch, area_f);
   note_launch();
   return check_launch("bwwk");
 }
 
 template <int K, int S>
 static int launch_bwwk_ks(const SeistOp& op, cudaStream_t s, int sm_count) {
-  if (op.Cout / op.groups <= 8) return launch_bwwk_t<K, S, 2>(op, s, sm_count);
-  return launch_bwwk_t<K, S, 4>(op, s, sm_count);
+  if (op.Cout / op.groups <= 8) return launch_bwwk_t<K, S, 2, 2>(op, s, sm_count);
+  // wide output tiles (32 channels, 8 per thread) halve the re-staging of the input rows; the 4*K extra
+  // accumulator registers fit for the short filters only
+  if constexpr (K <= 7 && S == 1) {
+    if (op.Cout / op.groups >= 32) return launch_bwwk_t<K, S, 4, 4>(op, s, sm_count);
+  }
+  return launch_bwwk_t<K, S, 4, 2>(op, s, sm_count);
 }
 
 static bool bwwk_has(int k, int stride) {
