@@ -58,12 +58,13 @@ int launch_convk_bwd_data(const SeistOp& op, cudaStream_t s);
 int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s);
 int launch_stem_compose(const SeistOp& op, bool fwd, cudaStream_t s);
 
-// tensor-core (tcgen05) path for the 1x1 forward.  SEIST_TC=0: never; SEIST_TC=1: every eligible op; default:
-// where it measured faster than the streaming SIMT kernel on B200 (profiles/): GELU-prologue inputs (the
-// activation is evaluated once per element instead of once per 16 output channels) and wide contractions.
+// tensor-core (tcgen05) paths (pw_tc.cu forward, bww_tc.cu weight gradient): validated against the interpreter
+// (tests/test_gpu_ops.py::test_tcgen05_kernels_match_interpreter) but, since the SIMT kernels moved to FFMA2 and
+// 4 CTAs/SM, slower than them on every op of the model family (profiles/r1_tc_vs_simt.txt) - opt-in:
+// SEIST_TC=1 every eligible op, SEIST_TC=2 the former heuristic (GELU-input / wide contractions), default never.
 static int tc_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = std::getenv("SEIST_TC"); v = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)); }
+  if (v < 0) { const char* e = std::getenv("SEIST_TC"); v = !e ? 0 : (e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0)); }
   return v;
 }
 // sliding-window weight-gradient kernel for k > 1 (bwwk.cu); SEIST_BWWK=0 falls back to the row-tiled kernel (A/B runs)

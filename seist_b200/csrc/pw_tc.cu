@@ -300,13 +300,30 @@ __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant_
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float s1[16], s2[16];
+        // element dropout: the 4 lanes of a sample quad share one hash per channel (common.cuh::keep4), so each
+        // lane hashes ONE channel of every group of 4 and the group exchanges the results with shuffles
+        uint64_t hq[4] = {0ull, 0ull, 0ull, 0ull};
+        if (F_ELEM) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int ck = min(c0 + 4 * g + (lane & 3), Cout - 1);
+            hq[g] = rng_u64(seed, op.seed_elem, (((uint64_t)n * Cout + ck) * (uint64_t)L + (ok ? l : 0)) >> 2);
+          }
+        }
+        const uint32_t thr = drop_threshold(op.p_elem);
+        const float keep_s = 1.0f / (1.0f - op.p_elem);
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const int co = c0 + c;
           float val = 0.f;
+          float kf = 1.f;
+          if (F_ELEM) {
+            const uint64_t hh = __shfl_sync(0xffffffffu, hq[c >> 2], (lane & ~3) | (c & 3));
+            kf = ((uint32_t)(hh >> (16 * (l & 3))) & 0xFFFFu) >= thr ? keep_s : 0.f;
+          }
           if (ok && co < Cout) {
             val = (__uint_as_float(rr[c]) + ep_s[co]) * pf;
-            if (F_ELEM) val *= elem_factor(op, seed, n, co, l);
+            if (F_ELEM) val *= kf;
             if (F_RES) {
               if (ra) val += fmaf(ep_s[Cout + co], ra[(size_t)co * L], ep_s[2 * Cout + co]);
               val *= af;

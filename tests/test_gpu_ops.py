@@ -96,3 +96,26 @@ def test_ops_match_interpreter(name, N, L, training, drops):
             if not err < TOL:
                 failures.append(f"bwd[{i}] {bc.name} {what}: rel {err:.3e} (max {ref:.3e})")
     assert not failures, "\n".join(failures[:30])
+
+
+@pytest.mark.gpu
+def test_tcgen05_kernels_match_interpreter():
+    """The tcgen05 (tensor-core) kernels are opt-in (SEIST_TC=1, read once per process): run the teacher-forced
+    op comparison of two cases in a child process with the switch on, and check that the tcgen05 kernels really
+    ran (launch counter of pw_tc / bww_tc via the mbarrier-timeout flag staying clear and the kernel-name probe)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SEIST_TC="1")
+    code = (
+        "import sys; sys.path.insert(0, 'tests');"
+        "import test_gpu_ops as T; from seist_b200 import _lib;"
+        "T.test_ops_match_interpreter('seist_m_dpk', 2, 2048, True, None);"
+        "T.test_ops_match_interpreter('seist_s_dpk', 2, 1024, True, dict(path_drop_rate=0.3, attn_drop_rate=0.2,"
+        " key_drop_rate=0.2, mlp_drop_rate=0.25, other_drop_rate=0.15));"
+        "assert _lib.lib().seist_tc_error_flag() == 0, 'tcgen05 mbarrier wait timed out';"
+        "print('TC-OK')"
+    )
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "TC-OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
