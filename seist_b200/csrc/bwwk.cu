@@ -35,7 +35,7 @@ struct BkOut {
 }  // namespace
 
 template <int K, int S, int TGM, int NPR>   // NPR pair rows (2*NPR output channels) per thread
-__global__ void __launch_bounds__(BK_NT, 2) bwwk_kernel(const __grid_constant__ SeistOp op, const int CI_B, const int PC,
+__global__ void __launch_bounds__(BK_NT, (K <= 9 && NPR == 2) ? 3 : 2) bwwk_kernel(const __grid_constant__ SeistOp op, const int CI_B, const int PC,
                                                         const int pitch, const int area_f) {
   constexpr int CO_B = 2 * NPR * TGM;
   constexpr int WN = K + 3 * S, WQ = (WN + 3) / 4;

@@ -94,7 +94,7 @@ __device__ __forceinline__ void ck_stage_input(const SeistOp& op, int n, int ci0
 // forward
 // ================================================================================================
 template <int K, int S>
-__global__ void __launch_bounds__(CK_NT) convk_fwd_kernel(const __grid_constant__ SeistOp op, const int WC) {
+__global__ void __launch_bounds__(CK_NT, 3) convk_fwd_kernel(const __grid_constant__ SeistOp op, const int WC) {
   extern __shared__ __align__(16) float ck_smem[];
   const int WP = 8 / WC, CO_B = 8 * WC, TLo = 128 * WP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -703,7 +703,7 @@ constexpr int BW_NT = 256;
 
 // BW_PC = output samples per chunk (128, or 512 for narrow tiles where the per-chunk barriers/latency dominate)
 template <int CO_B, int R_B, bool K1, int BW_PC>
-__global__ void __launch_bounds__(BW_NT) bww_kernel(const __grid_constant__ SeistOp op, const int nci_max) {
+__global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ SeistOp op, const int nci_max) {
   constexpr int BW_PITCH = BW_PC + 4;   // input row pitch (floats), keeps 16-byte alignment
   constexpr int BW_GP = 2 * BW_PC + 8;  // gacc channel-PAIR row pitch: g_s[pr][2*s + half] (FFMA2 operand pairs)
   extern __shared__ __align__(16) unsigned char sm_raw[];
