@@ -62,6 +62,11 @@ int launch_stem_compose(const SeistOp& op, bool fwd, cudaStream_t s);
 // (tests/test_gpu_ops.py::test_tcgen05_kernels_match_interpreter) but, since the SIMT kernels moved to FFMA2 and
 // 4 CTAs/SM, slower than them on every op of the model family (profiles/r1_tc_vs_simt.txt) - opt-in:
 // SEIST_TC=1 every eligible op, SEIST_TC=2 the former heuristic (GELU-input / wide contractions), default never.
+int bww_waves() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("SEIST_BWW_WAVES"); v = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 2; }
+  return v;
+}
 static int tc_mode() {
   static int v = -1;
   if (v < 0) { const char* e = std::getenv("SEIST_TC"); v = !e ? 0 : (e[0] == '1' ? 1 : (e[0] == '2' ? 2 : 0)); }

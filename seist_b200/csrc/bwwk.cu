@@ -273,7 +273,7 @@ static int launch_bwwk_t(const SeistOp& op, cudaStream_t s, int sm_count) {
                       (op.up_src_L > 0 ? sizeof(float) * (size_t)CI_B * (width + 4) : 0) + 16;
   const int gy = op.groups * ((gs_out + CO_B - 1) / CO_B), gz = ntile;
   const long tiles = (long)op.N * ((op.L_out + PC - 1) / PC);
-  long gx = (2L * sm_count + gy * gz - 1) / (gy * gz);
+  long gx = ((long)bww_waves() * sm_count + gy * gz - 1) / (gy * gz);
   if (gx > tiles) gx = tiles;
   if (gx < 1) gx = 1;
   if (smem > 48 * 1024) {

@@ -13,6 +13,7 @@ namespace seist {
 
 // ---- launch bookkeeping (api.cu) -------------------------------------------------------------
 void note_launch();
+int bww_waves();   // resident CTAs per SM the persistent weight-gradient kernels are sized for (SEIST_BWW_WAVES, default 2)
 int check_launch(const char* what);
 void set_error(const char* msg);
 

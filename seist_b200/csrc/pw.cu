@@ -982,7 +982,7 @@ static int launch_bww_pc(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int R = (op.Cin / op.groups) * k;
   const int gy = op.groups * ((op.Cout / op.groups + CO_B - 1) / CO_B), gz = (R + R_B - 1) / R_B;
   const long tiles = (long)op.N * ((op.L_out + BW_PC - 1) / BW_PC);
-  long gx = (2L * sm_count + gy * gz - 1) / (gy * gz);
+  long gx = ((long)bww_waves() * sm_count + gy * gz - 1) / (gy * gz);
   if (gx > tiles) gx = tiles;
   if (gx < 1) gx = 1;
   int rc = pw_set_smem(bww_kernel<CO_B, R_B, K1, BW_PC>, smem);

@@ -11,6 +11,7 @@ The per-step host syncs of the reference (`.item()`, barrier; train.py:124-135) 
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -140,7 +141,12 @@ class Trainer:
                 torch.cuda.synchronize()
                 self.launches_per_step = int(_lib.lib().seist_launch_count() - before)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # capture on a HIGH-priority stream: the forward/data-gradient chain is the critical path, the
+                # weight-gradient kernels forked onto the engine's default-priority side stream only fill the gaps
+                # (kernel nodes inherit the priority of the stream they were captured from)
+                prio = os.environ.get("SEIST_PRIO", "1") != "0"
+                cap = torch.cuda.Stream(device=self.x_static.device, priority=-1) if prio else None
+                with torch.cuda.graph(g, stream=cap):
                     self._issue()
                 self.graph = g
             else:
