@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libseist_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_IN = 3
 
 
@@ -59,6 +59,7 @@ HEADVEC_FWD, HEADVEC_BWD = 8, 9
 BN_FINALIZE_FWD, BN_FINALIZE_BWD, ZERO = 10, 11, 12
 BN_PREPARE_FWD, BN_PREPARE_BWD = 13, 14
 STEM_COMPOSE_FWD, STEM_COMPOSE_BWD = 15, 16
+GRAD_COMBINE = 17
 
 _lib = None
 

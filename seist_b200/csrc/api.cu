@@ -50,6 +50,7 @@ int pw_tc_error_flag();
 bool bww_tc_eligible(const SeistOp& op);
 int launch_bww_tc(const SeistOp& op, cudaStream_t s, int sm_count);
 bool bwwk_eligible(const SeistOp& op);
+int launch_grad_combine(const SeistOp& op, cudaStream_t s, int sm_count);
 bool convk_bwd_data_eligible(const SeistOp& op);
 int launch_bwwk(const SeistOp& op, cudaStream_t s, int sm_count);
 int bww_tc_error_flag();
@@ -124,6 +125,7 @@ static int run_one(const SeistOp& op, cudaStream_t s) {
     case SEIST_OP_BN_PREPARE_BWD: return launch_bn_prepare(op, false, s);
     case SEIST_OP_STEM_COMPOSE_FWD: return launch_stem_compose(op, true, s);
     case SEIST_OP_STEM_COMPOSE_BWD: return launch_stem_compose(op, false, s);
+    case SEIST_OP_GRAD_COMBINE: return launch_grad_combine(op, s, sm_count());
     case SEIST_OP_ZERO: {
       cudaError_t e = cudaMemsetAsync(op.out.x, 0, op.zero_bytes, s);
       if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }

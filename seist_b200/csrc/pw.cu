@@ -214,54 +214,71 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
     }
     if (!ok) continue;
     const float pf = path_factor(op, seed, n), af = alpha_factor(op, seed, n);
+    // output channels in batches of 4: the residual loads of a batch are issued before its first store (the
+    // compiler cannot move loads across possibly aliasing stores, which serialised load -> use -> store per channel)
 #pragma unroll
-    for (int col = 0; col < COUT_T; ++col) {
-      const int co = co_base + col;
-      if (co >= op.Cout) break;
-      const float2(&ap)[4] = acc[col >> 1];
-      float4 r = (col & 1) ? make_float4(ap[0].y, ap[1].y, ap[2].y, ap[3].y) : make_float4(ap[0].x, ap[1].x, ap[2].x, ap[3].x);
-      const float b = ep_s[col];
-      r.x = (r.x + b) * pf;
-      r.y = (r.y + b) * pf;
-      r.z = (r.z + b) * pf;
-      r.w = (r.w + b) * pf;
-      if (F_ELEM) {
-        const float4 kp = pw_keep4(op.p_elem, seed, op.seed_elem, ((uint64_t)n * op.Cout + co) * (uint64_t)L + l);
-        r.x *= kp.x;
-        r.y *= kp.y;
-        r.z *= kp.z;
-        r.w *= kp.w;
+    for (int cb = 0; cb < COUT_T; cb += 4) {
+      float4 ra[4], rb[4];
+      if (F_RES) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int co = min(co_base + cb + u, op.Cout - 1);
+          ra[u] = op.res_a.C > 0 ? ldg4(op.res_a.x + ((size_t)n * op.res_a.Ct + op.res_a.c0 + co) * (size_t)L + l)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          rb[u] = op.res_b.C > 0 ? ldg4(op.res_b.x + ((size_t)n * op.res_b.Ct + op.res_b.c0 + co) * (size_t)L + l)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-      if (F_RES && op.res_a.C > 0) {
-        const float4 a = ldg4(op.res_a.x + ((size_t)n * op.res_a.Ct + op.res_a.c0 + co) * (size_t)L + l);
-        const float sc = ep_s[COUT_T + col], sh = ep_s[2 * COUT_T + col];
-        r.x += fmaf(sc, a.x, sh);
-        r.y += fmaf(sc, a.y, sh);
-        r.z += fmaf(sc, a.z, sh);
-        r.w += fmaf(sc, a.w, sh);
-      }
-      r.x *= af;
-      r.y *= af;
-      r.z *= af;
-      r.w *= af;
-      if (F_RES && op.res_b.C > 0) {
-        const float4 a = ldg4(op.res_b.x + ((size_t)n * op.res_b.Ct + op.res_b.c0 + co) * (size_t)L + l);
-        const float sc = ep_s[3 * COUT_T + col], sh = ep_s[4 * COUT_T + col];
-        r.x += fmaf(sc, a.x, sh);
-        r.y += fmaf(sc, a.y, sh);
-        r.z += fmaf(sc, a.z, sh);
-        r.w += fmaf(sc, a.w, sh);
-      }
-      if (op.out_act == SEIST_OUT_SIGMOID) {
-        r.x = sigmoid_f(r.x);
-        r.y = sigmoid_f(r.y);
-        r.z = sigmoid_f(r.z);
-        r.w = sigmoid_f(r.w);
-      }
-      st4(op.out.x + ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l, r);
-      if (stats) {
-        my_st[(2 * col) * 32] += (r.x + r.y) + (r.z + r.w);
-        my_st[(2 * col + 1) * 32] += fmaf(r.x, r.x, r.y * r.y) + fmaf(r.z, r.z, r.w * r.w);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int col = cb + u;
+        const int co = co_base + col;
+        if (co >= op.Cout) break;
+        const float2(&ap)[4] = acc[col >> 1];
+        float4 r = (col & 1) ? make_float4(ap[0].y, ap[1].y, ap[2].y, ap[3].y) : make_float4(ap[0].x, ap[1].x, ap[2].x, ap[3].x);
+        const float b = ep_s[col];
+        r.x = (r.x + b) * pf;
+        r.y = (r.y + b) * pf;
+        r.z = (r.z + b) * pf;
+        r.w = (r.w + b) * pf;
+        if (F_ELEM) {
+          const float4 kp = pw_keep4(op.p_elem, seed, op.seed_elem, ((uint64_t)n * op.Cout + co) * (uint64_t)L + l);
+          r.x *= kp.x;
+          r.y *= kp.y;
+          r.z *= kp.z;
+          r.w *= kp.w;
+        }
+        if (F_RES && op.res_a.C > 0) {
+          const float4 a = ra[u];
+          const float sc = ep_s[COUT_T + col], sh = ep_s[2 * COUT_T + col];
+          r.x += fmaf(sc, a.x, sh);
+          r.y += fmaf(sc, a.y, sh);
+          r.z += fmaf(sc, a.z, sh);
+          r.w += fmaf(sc, a.w, sh);
+        }
+        r.x *= af;
+        r.y *= af;
+        r.z *= af;
+        r.w *= af;
+        if (F_RES && op.res_b.C > 0) {
+          const float4 a = rb[u];
+          const float sc = ep_s[3 * COUT_T + col], sh = ep_s[4 * COUT_T + col];
+          r.x += fmaf(sc, a.x, sh);
+          r.y += fmaf(sc, a.y, sh);
+          r.z += fmaf(sc, a.z, sh);
+          r.w += fmaf(sc, a.w, sh);
+        }
+        if (op.out_act == SEIST_OUT_SIGMOID) {
+          r.x = sigmoid_f(r.x);
+          r.y = sigmoid_f(r.y);
+          r.z = sigmoid_f(r.z);
+          r.w = sigmoid_f(r.w);
+        }
+        st4(op.out.x + ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l, r);
+        if (stats) {
+          my_st[(2 * col) * 32] += (r.x + r.y) + (r.z + r.w);
+          my_st[(2 * col + 1) * 32] += fmaf(r.x, r.x, r.y * r.y) + fmaf(r.z, r.z, r.w * r.w);
+        }
       }
     }
   }
@@ -283,6 +300,7 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
 // backward (data): d in[ci] = sum_co W[co][ci] gacc[co];  gacc = dOut * alpha * delta * D
 // dOut = A*du + Bx*x + Cc + dxd (then sigmoid').  grid (ceil(NQ/(128*G)), ceil(Cin/CI_T))
 // ================================================================================================
+constexpr int PW_BD_EB = 4;   // target channels whose epilogue loads are issued together
 constexpr int PW_BD_CG = 2;   // output channels whose gradient loads are in flight together (register budget: 4 CTAs/SM)
 struct PwOut {   // per output channel of the forward op, resolved once per CTA
   float A, Bx, Cc;
@@ -395,76 +413,95 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
       }
     }
     if (!ok) continue;
+    if constexpr (F_POOL) {
 #pragma unroll
-    for (int col = 0; col < CI_T; ++col) {
-      const PwChan& c = ch_s[col];
-      if (c.g == nullptr) continue;
-      const float2(&ap)[4] = acc[col >> 1];
-      float4 gg = (col & 1) ? make_float4(ap[0].y, ap[1].y, ap[2].y, ap[3].y) : make_float4(ap[0].x, ap[1].x, ap[2].x, ap[3].x);
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (F_POOL) {
-        // route the 4 pooled gradients to their 4*P source samples: g * (1/P + [first arg max])
-        const int P = op.pool;
-        const long long soff = (long long)n * c.nstride + (long long)l * P;
-        const float gq[4] = {gg.x, gg.y, gg.z, gg.w};
-        const float invp = 1.f / (float)P;
-        float s1 = 0.f, s2 = 0.f;
+      for (int col = 0; col < CI_T; ++col) {
+        const PwChan& c = ch_s[col];
+        if (c.g == nullptr) continue;
+        const float2(&ap)[4] = acc[col >> 1];
+        float4 gg = (col & 1) ? make_float4(ap[0].y, ap[1].y, ap[2].y, ap[3].y) : make_float4(ap[0].x, ap[1].x, ap[2].x, ap[3].x);
+        {
+          // route the 4 pooled gradients to their 4*P source samples: g * (1/P + [first arg max])
+          const int P = op.pool;
+          const long long soff = (long long)n * c.nstride + (long long)l * P;
+          const float gq[4] = {gg.x, gg.y, gg.z, gg.w};
+          const float invp = 1.f / (float)P;
+          float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float* xs = c.x + soff + j * P;
-          float* gs = c.g + soff + j * P;
-          int am = 0;
-          float mx = -INFINITY;
-          for (int i = 0; i < P; ++i) {
-            const float u = fmaf(c.sc, __ldg(xs + i), c.sh);
-            if (u > mx) {
-              mx = u;
-              am = i;
+          for (int j = 0; j < 4; ++j) {
+            const float* xs = c.x + soff + j * P;
+            float* gs = c.g + soff + j * P;
+            int am = 0;
+            float mx = -INFINITY;
+            for (int i = 0; i < P; ++i) {
+              const float u = fmaf(c.sc, __ldg(xs + i), c.sh);
+              if (u > mx) {
+                mx = u;
+                am = i;
+              }
+            }
+            for (int i = 0; i < P; i += 2) {   // P is even: pairs keep the stores 8-byte wide
+              float2 g2 = make_float2(gq[j] * (invp + (i == am ? 1.f : 0.f)), gq[j] * (invp + (i + 1 == am ? 1.f : 0.f)));
+              const float2 x2 = __ldg(reinterpret_cast<const float2*>(xs + i));
+              s1 += g2.x + g2.y;
+              s2 = fmaf(g2.x, (x2.x - c.mu) * c.istd, fmaf(g2.y, (x2.y - c.mu) * c.istd, s2));
+              if (c.accum) {
+                const float2 old = *reinterpret_cast<const float2*>(gs + i);
+                g2.x += old.x;
+                g2.y += old.y;
+              }
+              *reinterpret_cast<float2*>(gs + i) = g2;
             }
           }
-          for (int i = 0; i < P; i += 2) {   // P is even: pairs keep the stores 8-byte wide
-            float2 g2 = make_float2(gq[j] * (invp + (i == am ? 1.f : 0.f)), gq[j] * (invp + (i + 1 == am ? 1.f : 0.f)));
-            const float2 x2 = __ldg(reinterpret_cast<const float2*>(xs + i));
-            s1 += g2.x + g2.y;
-            s2 = fmaf(g2.x, (x2.x - c.mu) * c.istd, fmaf(g2.y, (x2.y - c.mu) * c.istd, s2));
-            if (c.accum) {
-              const float2 old = *reinterpret_cast<const float2*>(gs + i);
-              g2.x += old.x;
-              g2.y += old.y;
-            }
-            *reinterpret_cast<float2*>(gs + i) = g2;
+          if (c.bn >= 0) {
+            my_st[(2 * col) * 32] += s1;
+            my_st[(2 * col + 1) * 32] += s2;
           }
+        }
+      }
+    } else {
+    // targets in batches of PW_BD_EB channels: all loads of a batch (x for khat / GELU', the old gradient when
+    // accumulating) are issued before its first store, so their latency overlaps instead of serialising
+    // load -> use -> store once per channel (the compiler cannot hoist loads over possibly aliasing stores)
+#pragma unroll
+    for (int cb = 0; cb < CI_T; cb += PW_BD_EB) {
+      float4 xv[PW_BD_EB], ov[PW_BD_EB];
+#pragma unroll
+      for (int u = 0; u < PW_BD_EB; ++u) {
+        const PwChan& c = ch_s[cb + u];
+        const long long off = (long long)n * c.nstride + l;
+        const bool live = c.g != nullptr;
+        xv[u] = (live && ((F_GELU && c.act == SEIST_ACT_GELU) || c.bn >= 0)) ? ldg4(c.x + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ov[u] = (live && c.accum) ? ld4(c.g + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < PW_BD_EB; ++u) {
+        const int col = cb + u;
+        const PwChan& c = ch_s[col];
+        if (c.g == nullptr) continue;
+        const float2(&ap)[4] = acc[col >> 1];
+        float4 gg = (col & 1) ? make_float4(ap[0].y, ap[1].y, ap[2].y, ap[3].y) : make_float4(ap[0].x, ap[1].x, ap[2].x, ap[3].x);
+        const float4 x = xv[u];
+        if (F_GELU && c.act == SEIST_ACT_GELU) {
+          const float4 d = pw_gelu_grad4(make_float4(fmaf(c.sc, x.x, c.sh), fmaf(c.sc, x.y, c.sh), fmaf(c.sc, x.z, c.sh),
+                                                     fmaf(c.sc, x.w, c.sh)));
+          gg.x *= d.x;
+          gg.y *= d.y;
+          gg.z *= d.z;
+          gg.w *= d.w;
         }
         if (c.bn >= 0) {
-          my_st[(2 * col) * 32] += s1;
-          my_st[(2 * col + 1) * 32] += s2;
+          my_st[(2 * col) * 32] += (gg.x + gg.y) + (gg.z + gg.w);
+          my_st[(2 * col + 1) * 32] += fmaf(gg.x, (x.x - c.mu) * c.istd, gg.y * ((x.y - c.mu) * c.istd)) +
+                                       fmaf(gg.z, (x.z - c.mu) * c.istd, gg.w * ((x.w - c.mu) * c.istd));
         }
-        continue;
+        gg.x += ov[u].x;
+        gg.y += ov[u].y;
+        gg.z += ov[u].z;
+        gg.w += ov[u].w;
+        st4(c.g + (long long)n * c.nstride + l, gg);
       }
-      const long long off = (long long)n * c.nstride + l;
-      if ((F_GELU && c.act == SEIST_ACT_GELU) || c.bn >= 0) x = ldg4(c.x + off);
-      if (F_GELU && c.act == SEIST_ACT_GELU) {
-        const float4 d = pw_gelu_grad4(make_float4(fmaf(c.sc, x.x, c.sh), fmaf(c.sc, x.y, c.sh), fmaf(c.sc, x.z, c.sh),
-                                                   fmaf(c.sc, x.w, c.sh)));
-        gg.x *= d.x;
-        gg.y *= d.y;
-        gg.z *= d.z;
-        gg.w *= d.w;
-      }
-      if (c.bn >= 0) {
-        my_st[(2 * col) * 32] += (gg.x + gg.y) + (gg.z + gg.w);
-        my_st[(2 * col + 1) * 32] += fmaf(gg.x, (x.x - c.mu) * c.istd, gg.y * ((x.y - c.mu) * c.istd)) +
-                                     fmaf(gg.z, (x.z - c.mu) * c.istd, gg.w * ((x.w - c.mu) * c.istd));
-      }
-      float* gp = c.g + off;
-      if (c.accum) {
-        const float4 old = ld4(gp);
-        gg.x += old.x;
-        gg.y += old.y;
-        gg.z += old.z;
-        gg.w += old.w;
-      }
-      st4(gp, gg);
+    }
     }
   }
   float st[2 * CI_T];
@@ -677,6 +714,59 @@ int launch_pw_bwd_data(const SeistOp& op, cudaStream_t s, int sm_count) {
   if (rc) return rc;
   note_launch();
   return check_launch("pw_bwd_data");
+}
+
+// ================================================================================================
+// GRAD_COMBINE: BatchNorm backward of the output gradient, once and in place (out.g <- A*out.g + Bx*x + Cc
+// [+ dxd]); grid (ceil(NQ/(128*G)), C).  The backward ops of the same conv then read a plain gradient.
+// ================================================================================================
+__global__ void __launch_bounds__(PW_NT) grad_combine_kernel(const __grid_constant__ SeistOp op, const int G) {
+  const int co = blockIdx.y;
+  const int L = op.out.L;
+  const OutGradCoef kc = out_grad_coef(op, co);
+  const size_t row = (size_t)op.out.Ct * L, base = (size_t)(op.out.c0 + co) * L;
+  if ((L & 3) == 0) {
+    const int LQ = L >> 2;
+    const long long NQ = (long long)op.N * LQ;
+    for (int g = 0; g < G; ++g) {
+      const long long f = ((long long)blockIdx.x * G + g) * PW_NT + threadIdx.x;
+      if (f >= NQ) break;
+      const int n = (int)(f / LQ);
+      const int l = (int)(f - (long long)n * LQ) * 4;
+      const size_t off = (size_t)n * row + base + l;
+      const float4 du = ld4(op.out.g + off), x = ldg4(op.out.x + off);
+      float4 r = op.out_dxd ? ldg4(op.out_dxd + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      r.x += fmaf(kc.A, du.x, fmaf(kc.Bx, x.x, kc.Cc));
+      r.y += fmaf(kc.A, du.y, fmaf(kc.Bx, x.y, kc.Cc));
+      r.z += fmaf(kc.A, du.z, fmaf(kc.Bx, x.z, kc.Cc));
+      r.w += fmaf(kc.A, du.w, fmaf(kc.Bx, x.w, kc.Cc));
+      st4(op.out.g + off, r);
+    }
+  } else {
+    const long long NE = (long long)op.N * L;
+    for (int g = 0; g < 4 * G; ++g) {
+      const long long f = ((long long)blockIdx.x * 4 * G + g) * PW_NT + threadIdx.x;
+      if (f >= NE) break;
+      const int n = (int)(f / L);
+      const size_t off = (size_t)n * row + base + (size_t)(f - (long long)n * L);
+      float r = op.out_dxd ? op.out_dxd[off] : 0.f;
+      r += fmaf(kc.A, op.out.g[off], fmaf(kc.Bx, op.out.x[off], kc.Cc));
+      op.out.g[off] = r;
+    }
+  }
+}
+
+int launch_grad_combine(const SeistOp& op, cudaStream_t s, int sm_count) {
+  if (op.out.bn < 0 || op.out.g == nullptr) {
+    set_error("GRAD_COMBINE: the output view has no BatchNorm gradient");
+    return -4;
+  }
+  const long long nq = ((long long)op.N * op.out.L + 3) / 4;
+  const int G = pick_G(nq, op.out.C, sm_count);
+  dim3 grid((unsigned)((nq + (long long)PW_NT * G - 1) / ((long long)PW_NT * G)), op.out.C);
+  grad_combine_kernel<<<grid, PW_NT, 0, s>>>(op, G);
+  note_launch();
+  return check_launch("grad_combine");
 }
 
 int launch_res_bwd4(const SeistOp& op, cudaStream_t s, int sm_count) {

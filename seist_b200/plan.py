@@ -14,6 +14,7 @@ Reference semantics cited per emitter (paths relative to /root/reference/models/
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -120,6 +121,7 @@ class Op:
     n_bn: int = 0
     name: str = ""
     fwd: Optional["Op"] = None            # backward ops point at their forward op
+    combined: bool = False                # forward op whose output gradient is BN-backward-combined in place (GRAD_COMBINE)
     sync_bn: List[int] = field(default_factory=list)  # BN indices whose (g)stat must be all-reduced BEFORE this op
 
 
@@ -519,6 +521,9 @@ class PlanBuilder:
         for f in reversed(pl.fwd_ops):
             if f.kind == _lib.CONV_FWD:
                 up_atomic = f.up_src_L > 0
+                if self._wants_combine(f):
+                    f.combined = True
+                    ops.append(Op(_lib.GRAD_COMBINE, f.N, out=f.out, fwd=f, name=f.name + ":gcomb"))
                 if f.res_a is not None or f.res_b is not None:
                     ra, rb = grad_target(f.res_a), grad_target(f.res_b)
                     if ra is not None or rb is not None:
@@ -547,6 +552,17 @@ class PlanBuilder:
                 pass
         ops.append(Op(_lib.BN_FINALIZE_BWD, self.N, name="bn_finalize_bwd"))
 
+    @staticmethod
+    def _wants_combine(f: Op) -> bool:
+        """Evaluate the BN backward of f's output once (GRAD_COMBINE) instead of in every pass of its three
+        backward ops?  Pays off when the data gradient needs several 16-channel passes over the output gradient
+        (wide 1x1 convs): each pass then loads one tensor instead of (du, x[, dxd]).  SEIST_COMBINE_CIN sets the
+        minimum reduction width (0 disables)."""
+        thr = int(os.environ.get("SEIST_COMBINE_CIN", "32"))
+        if thr <= 0 or f.out is None or f.out.bn < 0 or not f.out.buf.need_du:
+            return False
+        return f.k == 1 and f.stride == 1 and f.groups == 1 and f.Cin >= thr
+
     def _insert_prepares(self, ops: List[Op], forward: bool) -> List[Op]:
         """Insert the BN_PREPARE ops: the per-channel coefficient table of a BN is computed once, after its
         last producer and before its first consumer (forward: scale/shift/khat from the batch statistics;
@@ -564,7 +580,7 @@ class PlanBuilder:
                 for v in list(op.ins) + [op.res_a, op.res_b]:
                     if v is not None and v.buf is not None and v.bn >= 0:
                         needs.add(v.bn)
-            elif op.kind in (_lib.CONV_BWD_DATA, _lib.CONV_BWD_W, _lib.RES_BWD) and op.out.bn >= 0 \
+            elif op.kind in (_lib.CONV_BWD_DATA, _lib.CONV_BWD_W, _lib.RES_BWD, _lib.GRAD_COMBINE) and op.out.bn >= 0 \
                     and op.out.buf.need_du:
                 needs.add(op.out.bn)
             todo = sorted(b for b in needs if b not in ready)
@@ -699,6 +715,9 @@ def to_c(plan: Plan, ops: List[Op]):
             if bw and ob is not None:
                 c.out.g = _ptr(ob.du) if op.out.bn >= 0 else 0
                 c.out_dxd = _ptr(ob.dxd)
+                if f.combined and op.kind != _lib.GRAD_COMBINE:
+                    # the output gradient was combined in place by GRAD_COMBINE: a plain gradient in `du`
+                    c.out.bn, c.out.g, c.out_dxd = -1, 0, _ptr(ob.du)
         if op.kind == _lib.ZERO:
             t = op.out.buf.du if op.out.bn >= 0 else op.out.buf.dxd
             assert op.out.c0 == 0 and op.out.C == op.out.buf.C, "ZERO clears whole buffers only"
