@@ -301,6 +301,63 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_c
   const int pq = p0 + wp * 128 + 4 * lane;
   float st[16];
 #pragma unroll
+  for (int i = 0; i < 16; ++i) st[i] = 0.f;
+  // fast path (whole quads inside the row, no up-sampling): 16-byte accesses, and the loads of a batch of
+  // channels (x for khat / GELU', the old gradient when accumulating) are all issued before its first store
+  const int pos0 = S == 2 ? 2 * pq : pq;
+  const bool fast = op.up_src_L == 0 && (op.L_in & 3) == 0 && pos0 + 4 * S - 1 < op.L_in;
+  if (fast) {
+    const SeistView& v = op.in[0];          // convk ops have a single input view
+    if (v.g != nullptr) {
+      constexpr int NV = S == 2 ? 2 : 1;    // float4 per real channel
+      constexpr int CB = S == 2 ? 2 : 4;    // real channels per batch (4 x-loads + 4 old-loads in flight)
+      const bool need_x = v.act == SEIST_ACT_GELU || v.bn >= 0;
+#pragma unroll
+      for (int kb = 0; kb < CPW; kb += CB) {
+        float4 xv[CB * NV], ov[CB * NV];
+#pragma unroll
+        for (int u = 0; u < CB; ++u) {
+          const int ci = min(ci_base + wc * CPW + kb + u, ci_end - 1);
+          const size_t off = ((size_t)n * v.Ct + v.c0 + ci) * (size_t)v.L + pos0;
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            xv[u * NV + q] = need_x ? __ldg(reinterpret_cast<const float4*>(v.x + off) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ov[u * NV + q] = v.accum ? *(reinterpret_cast<const float4*>(v.g + off) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < CB; ++u) {
+          const int k = kb + u;
+          const int ci = ci_base + wc * CPW + k;
+          if (ci >= ci_end) continue;
+          float sc, sh, mu = 0.f, istd = 0.f;
+          view_coef(op, v, ci, sc, sh);
+          if (v.bn >= 0) view_khat(op, v, ci, mu, istd);
+          const size_t off = ((size_t)n * v.Ct + v.c0 + ci) * (size_t)v.L + pos0;
+#pragma unroll
+          for (int q = 0; q < NV; ++q) {
+            const float4 x4 = xv[u * NV + q], o4 = ov[u * NV + q];
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+            const float os[4] = {o4.x, o4.y, o4.z, o4.w};
+            float g[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // S = 1: element e is sample j = e of channel k; S = 2: element 4q+e is (j, parity) = ((4q+e)>>1, e&1)
+              const int c = S == 2 ? 2 * k + (e & 1) : k;
+              const int j = S == 2 ? (4 * q + e) >> 1 : e;
+              float gv = ck_acc(acc, c, j);
+              if (v.act == SEIST_ACT_GELU) gv *= gelu_grad_f(fmaf(sc, xs[e], sh));
+              st[2 * c] += gv;
+              st[2 * c + 1] = fmaf(gv, (xs[e] - mu) * istd, st[2 * c + 1]);
+              g[e] = gv + os[e];
+            }
+            *(reinterpret_cast<float4*>(v.g + off) + q) = make_float4(g[0], g[1], g[2], g[3]);
+          }
+        }
+      }
+    }
+  } else
+#pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int ci = ci_base + wc * CPW + (S == 2 ? (c >> 1) : c);
     float s1 = 0.f, s2 = 0.f;

@@ -556,9 +556,10 @@ class PlanBuilder:
     def _wants_combine(f: Op) -> bool:
         """Evaluate the BN backward of f's output once (GRAD_COMBINE) instead of in every pass of its three
         backward ops?  Pays off when the data gradient needs several 16-channel passes over the output gradient
-        (wide 1x1 convs): each pass then loads one tensor instead of (du, x[, dxd]).  SEIST_COMBINE_CIN sets the
-        minimum reduction width (0 disables)."""
-        thr = int(os.environ.get("SEIST_COMBINE_CIN", "32"))
+        (wide 1x1 convs): each pass then loads one tensor instead of (du, x[, dxd]).  Measured on B200 it is a wash
+        (the combine passes cost what the backward ops save, profiles/), so it is OFF by default; SEIST_COMBINE_CIN=<min
+        reduction width> enables it."""
+        thr = int(os.environ.get("SEIST_COMBINE_CIN", "0"))
         if thr <= 0 or f.out is None or f.out.bn < 0 or not f.out.buf.need_du:
             return False
         return f.k == 1 and f.stride == 1 and f.groups == 1 and f.Cin >= thr

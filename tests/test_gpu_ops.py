@@ -99,6 +99,15 @@ def test_ops_match_interpreter(name, N, L, training, drops):
 
 
 @pytest.mark.gpu
+def test_grad_combine_ops_match_interpreter(monkeypatch):
+    """GRAD_COMBINE (BN backward of the output gradient evaluated once, in place) is opt-in: compile the plans with
+    it enabled for every 1x1 conv of width >= 16 and run the same op-by-op comparison."""
+    monkeypatch.setenv("SEIST_COMBINE_CIN", "16")
+    test_ops_match_interpreter("seist_m_dpk", 2, 2048, True, None)
+    test_ops_match_interpreter("seist_s_dpk", 3, 1000, True, None)      # ragged length: scalar combine path
+
+
+@pytest.mark.gpu
 def test_tcgen05_kernels_match_interpreter():
     """The tcgen05 (tensor-core) kernels are opt-in (SEIST_TC=1, read once per process): run the teacher-forced
     op comparison of two cases in a child process with the switch on, and check that the tcgen05 kernels really
