@@ -356,6 +356,69 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_c
         }
       }
     }
+  } else if (S == 1 && op.up_src_L > 0 && 2 * Lsrc == op.L_in && (op.L_in & 3) == 0) {
+    // exact x2 linear up-sampling (the dpk head, reference models/seist.py:566): the quad p = 4m .. 4m+3 only touches
+    // the sources 2m-1 .. 2m+2 with the fixed weights (.25 | .75 .75 .25 | .25 .75 .75 | .25).  Every lane owns the
+    // sources 2m, 2m+1: the two outer contributions travel to the neighbouring lanes by shuffle, the activation
+    // derivative and the BN sums are evaluated once per SOURCE sample, and 2 (+1 at a warp edge) atomics per
+    // channel replace 8 (the target is zero-initialised by the preceding ZERO op).
+    const SeistView& v = op.in[0];
+    if (v.g != nullptr) {
+      const bool inside = pq < op.L_in;
+      const int m2 = pq >> 1;                               // source index 2m
+      const bool first = pq == 0, last = pq + 4 >= op.L_in;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int ci = ci_base + wc * 8 + c;
+        const bool live = ci < ci_end;                      // warp-uniform
+        const float d0 = inside && live ? ck_acc(acc, c, 0) : 0.f, d1 = inside && live ? ck_acc(acc, c, 1) : 0.f;
+        const float d2 = inside && live ? ck_acc(acc, c, 2) : 0.f, d3 = inside && live ? ck_acc(acc, c, 3) : 0.f;
+        float ga = 0.25f * d0, ge = 0.25f * d3;             // to 2m-1 / 2m+2
+        float gb = 0.75f * (d0 + d1) + 0.25f * d2, gc = 0.25f * d1 + 0.75f * (d2 + d3);
+        if (first) {
+          gb += ga;
+          ga = 0.f;
+        }
+        if (last) {
+          gc += ge;
+          ge = 0.f;
+        }
+        const float from_prev = __shfl_up_sync(0xffffffffu, ge, 1), from_next = __shfl_down_sync(0xffffffffu, ga, 1);
+        if (lane > 0) gb += from_prev;
+        if (lane < 31) gc += from_next;
+        if (!live || !inside) continue;
+        float sc, sh, mu = 0.f, istd = 0.f;
+        view_coef(op, v, ci, sc, sh);
+        if (v.bn >= 0) view_khat(op, v, ci, mu, istd);
+        const float* xr = view_row(v, n, ci);
+        float* gr = view_grad_row(v, n, ci);
+        const float2 x2 = *reinterpret_cast<const float2*>(xr + m2);
+        if (v.act == SEIST_ACT_GELU) {
+          gb *= gelu_grad_f(fmaf(sc, x2.x, sh));
+          gc *= gelu_grad_f(fmaf(sc, x2.y, sh));
+        }
+        atomicAdd(&gr[m2], gb);
+        atomicAdd(&gr[m2 + 1], gc);
+        float s1 = gb + gc;
+        float s2 = fmaf(gb, (x2.x - mu) * istd, gc * ((x2.y - mu) * istd));
+        if (lane == 0 && !first) {                           // 2m-1 belongs to the last lane of another warp
+          const float xa = xr[m2 - 1];
+          if (v.act == SEIST_ACT_GELU) ga *= gelu_grad_f(fmaf(sc, xa, sh));
+          atomicAdd(&gr[m2 - 1], ga);
+          s1 += ga;
+          s2 = fmaf(ga, (xa - mu) * istd, s2);
+        }
+        if (lane == 31 && !last) {                           // 2m+2 belongs to the first lane of another warp
+          const float xe = xr[m2 + 2];
+          if (v.act == SEIST_ACT_GELU) ge *= gelu_grad_f(fmaf(sc, xe, sh));
+          atomicAdd(&gr[m2 + 2], ge);
+          s1 += ge;
+          s2 = fmaf(ge, (xe - mu) * istd, s2);
+        }
+        st[2 * c] = s1;
+        st[2 * c + 1] = s2;
+      }
+    }
   } else
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
