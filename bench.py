@@ -221,11 +221,16 @@ def main():
     # ---- end to end: pinned host inputs in, loss out, every step ----------------------------------
     loss_host = torch.zeros((), pin_memory=True)
 
+    # every step: one pinned-host -> device copy of a full batch (issued on the trainer's copy stream right after
+    # the step that consumes the previous one was launched, so it overlaps that step - the job of a data loader's
+    # prefetcher) and one device -> host read of the step's loss, waited for before the next step starts
     def e2e_step():
-        loss = trainer.step(x_h, t_h)
+        loss = trainer.step()                      # consumes the staged batch
+        trainer.prefetch(x_h, t_h)                 # H2D of the next batch, overlapping the step just launched
         loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    trainer.prefetch(x_h, t_h)
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
@@ -272,7 +277,8 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                        "h2d_bytes_per_step": (x_h.numel() + t_h.numel()) * 4, "d2h_bytes_per_step": 4},
+                        "h2d_bytes_per_step": (x_h.numel() + t_h.numel()) * 4, "d2h_bytes_per_step": 4,
+                        "h2d": "pinned host batch copied every step on a copy stream, one step ahead (Trainer.prefetch)"},
                 "gpu_launches": trainer.launches_per_step * args.steps,
                 "launches_per_step": trainer.launches_per_step, "cuda_graph": trainer.graph is not None,
                 "loss": loss_val, "clocks": clocks, "roofline": roofline, "step_roofline": step_roofline,

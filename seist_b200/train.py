@@ -126,12 +126,46 @@ class Trainer:
                                        self.step_t.data_ptr(), self.betas[0], self.betas[1], self.eps,
                                        self.weight_decay, 1 if self.decoupled else 0, gscale, s))
 
-    def step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        """x (N,3,L), target on the device (or pinned host tensors: copied with non_blocking=True)."""
-        if self._shape != (tuple(x.shape), tuple(target.shape)) or not self.flat.valid():
-            self._setup(x if x.is_cuda else x.cuda(non_blocking=True), target)
-        self.x_static.copy_(x, non_blocking=True)
-        self.t_static.copy_(target.reshape(self.t_static.shape), non_blocking=True)
+    # ---- input prefetch (the data-loader side of reference training/train.py:76-80) -------------------
+    def prefetch(self, x: torch.Tensor, target: torch.Tensor):
+        """Start the host -> device copy of the NEXT step's batch on a copy stream; it overlaps the step that is
+        running.  The following `step()` (called without arguments) consumes it.  Pinned host tensors make the
+        copy asynchronous (the reference moves batches with `.to(device)` inside the step instead)."""
+        if self._shape is None:
+            raise RuntimeError("prefetch() needs one step(x, target) first (it sizes the static buffers)")
+        if not hasattr(self, "_copy_stream"):
+            dev = self.x_static.device
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._x_stage = torch.empty_like(self.x_static)
+            self._t_stage = torch.empty_like(self.t_static)
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream())
+        cs = self._copy_stream
+        cs.wait_event(self._consumed)              # the previous staged batch has been moved into the plan's input
+        with torch.cuda.stream(cs):
+            self._x_stage.copy_(x, non_blocking=True)
+            self._t_stage.copy_(target.reshape(self._t_stage.shape), non_blocking=True)
+            self._staged.record(cs)
+        self._has_staged = True
+
+    def step(self, x: Optional[torch.Tensor] = None, target: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x (N,3,L), target on the device (or pinned host tensors: copied with non_blocking=True); without
+        arguments: the batch staged by `prefetch()`.  Returns the (device) loss of this step."""
+        if x is None:
+            if not getattr(self, "_has_staged", False):
+                raise RuntimeError("step() without arguments needs a prefetch()ed batch")
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._staged)
+            self.x_static.copy_(self._x_stage, non_blocking=True)      # device -> device, ~0.1 ms
+            self.t_static.copy_(self._t_stage, non_blocking=True)
+            self._consumed.record(cur)
+            self._has_staged = False
+        else:
+            if self._shape != (tuple(x.shape), tuple(target.shape)) or not self.flat.valid():
+                self._setup(x if x.is_cuda else x.cuda(non_blocking=True), target)
+            self.x_static.copy_(x, non_blocking=True)
+            self.t_static.copy_(target.reshape(self.t_static.shape), non_blocking=True)
         if self.lr_schedule is not None:
             self.lr_t.fill_(float(self.lr_schedule(self.it)))
         if self.use_graph and self.world == 1:

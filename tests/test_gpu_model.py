@@ -189,3 +189,24 @@ def test_full_size_batch_properties():
 
     mu_full, mu_a, mu_b = stem_mean(x), stem_mean(x[:N // 2].contiguous()), stem_mean(x[N // 2:].contiguous())
     assert (mu_full - 0.5 * (mu_a + mu_b)).abs().max().item() <= 1e-5 * (mu_full.abs().max().item() + 1e-3)
+
+
+@pytest.mark.gpu
+def test_trainer_prefetch_equals_direct_step():
+    """Trainer.prefetch() + step() (copy stream, one batch ahead) must train exactly like step(x, target)."""
+    import copy
+    from seist_b200.train import Trainer
+    g, m = _load("seist_s_dpk")
+    m2 = copy.deepcopy(m)
+    x, tgt = g["x"], g["target"]
+    xp, tp = x.pin_memory(), tgt.pin_memory()
+    ta, tb = Trainer(m, lr=1e-3), Trainer(m2, lr=1e-3)
+    la = [float(ta.step(x.cuda(), tgt.cuda())) for _ in range(3)]
+    lb = [float(tb.step(xp, tp))]
+    for _ in range(2):
+        tb.prefetch(xp, tp)
+        lb.append(float(tb.step()))
+    assert all(abs(a - b) <= 1e-5 * abs(a) for a, b in zip(la, lb)), (la, lb)
+    assert la[2] != la[0]                                  # the parameters really moved
+    with pytest.raises(RuntimeError):
+        tb.step()                                          # nothing staged
