@@ -190,7 +190,18 @@ class Trainer:
                 self.graph.replay()
         else:
             before = _lib.lib().seist_launch_count()
-            self._issue()
+            if os.environ.get("SEIST_PRIO", "1") != "0":
+                # same priority split as the captured graph: the step runs on a high-priority stream, the
+                # weight-gradient side stream (default priority) only fills what the main chain leaves idle
+                cur = torch.cuda.current_stream()
+                if getattr(self, "_hp_stream", None) is None:
+                    self._hp_stream = torch.cuda.Stream(device=self.x_static.device, priority=-1)
+                self._hp_stream.wait_stream(cur)
+                with torch.cuda.stream(self._hp_stream):
+                    self._issue()
+                cur.wait_stream(self._hp_stream)
+            else:
+                self._issue()
             self.launches_per_step = int(_lib.lib().seist_launch_count() - before)
         self.it += 1
         return self.loss_out
