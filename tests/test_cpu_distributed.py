@@ -4,7 +4,6 @@ slots exactly where the compiler placed the sync points; parameter gradients are
 flat all-reduce.  The result must equal ONE process on the concatenated batch — the reference's semantics
 for DDP + SyncBatchNorm with equal per-rank batches (training/train.py:369-374)."""
 import os
-import socket
 
 import pytest
 import torch
@@ -52,10 +51,10 @@ def _run(plan, x, dy, world):
     return y
 
 
-def _worker(rank, world, port, q):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _worker(rank, world, store_path, q):
+    # file rendezvous: no TCP port to race for (a port probed free by the parent can be taken before rank 0 binds it)
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+    dist.init_process_group("gloo", init_method=f"file://{store_path}", rank=rank, world_size=world)
     torch.manual_seed(0)
     x, tgt = R.synth_waveforms(NB, L, seed=3)
     m = _model()
@@ -93,12 +92,11 @@ def _run_forward_only(plan, x):
 
 
 def test_two_ranks_equal_one_process_on_concatenated_batch():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
+    import tempfile
+    store_path = os.path.join(tempfile.mkdtemp(prefix="seist_gloo_"), "rendezvous")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, store_path, q)) for r in range(2)]
     for p_ in procs:
         p_.start()
     y2, g2, rb2 = q.get(timeout=600)
