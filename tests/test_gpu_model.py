@@ -24,6 +24,25 @@ def _load(name):
     return g, m.cuda()
 
 
+def _detection_edges_match(y, ref, tol=1, amb=2e-3):
+    """the detection channel (0) has plateaus and exact ties, so it is compared through the end points
+    of its > 0.5 intervals, +-`tol` samples.  Edges where the reference itself is within `amb` of the threshold in
+    the neighbourhood are ambiguous under a 1e-3 output tolerance and skipped."""
+    def edges(v):
+        m = (v > 0.5).int()
+        return (m[1:] - m[:-1]).nonzero().flatten() + 1
+    for n in range(ref.shape[0]):
+        ea, eb = edges(y[n, 0]), edges(ref[n, 0])
+        for src, dst, base in ((eb, ea, ref[n, 0]), (ea, eb, ref[n, 0])):
+            for i in src.tolist():
+                lo, hi = max(i - 2, 0), min(i + 2, base.numel())
+                if (base[lo:hi] - 0.5).abs().min().item() < amb:
+                    continue
+                if dst.numel() == 0 or (dst - i).abs().min().item() > tol:
+                    return False
+    return True
+
+
 def _check_grads(model, ref_grads, rtol=2e-3, floor=1e-5):
     gmax = max(v.abs().max().item() for v in ref_grads.values())
     bad = []
@@ -48,6 +67,7 @@ def test_eval_matches_reference_golden(name):
     assert (y - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
     if name.endswith("dpk"):
         assert torch.equal(y[:, 1:].argmax(-1), ref[:, 1:].argmax(-1))   # P and S picks bit-exact
+        assert _detection_edges_match(y, ref)                             # detection intervals, +-1 sample
 
 
 @pytest.mark.gpu
