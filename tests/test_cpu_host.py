@@ -167,3 +167,21 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     L = _lib.lib()      # ABI version + struct layout checks (no GPU needed)
     assert L.seist_abi_version() == _lib.ABI_VERSION
+
+
+def test_cyclic_lr_matches_torch_scheduler():
+    """Trainer's host-side schedule must equal torch.optim.lr_scheduler.CyclicLR as the reference configures it
+    (training/train.py:343-354: exp_range, cycle_momentum=False, gamma = base_lr ** (1 / (2 * steps)))."""
+    from seist_b200.train import cyclic_lr
+    base, mx, up, down, steps = 8e-5, 1e-3, 20, 30, 120
+    gamma = base ** ((steps * 2) ** -1)
+    for mode, g in (("triangular", None), ("exp_range", gamma)):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([p], lr=base)
+        sch = torch.optim.lr_scheduler.CyclicLR(opt, base_lr=base, max_lr=mx, step_size_up=up, step_size_down=down,
+                                                mode=mode, gamma=gamma if g else 1.0, cycle_momentum=False)
+        for it in range(steps):
+            ref = opt.param_groups[0]["lr"]
+            assert abs(cyclic_lr(it, base, mx, up, down, g) - ref) <= 1e-9 + 1e-7 * ref, (mode, it)
+            opt.step()
+            sch.step()
