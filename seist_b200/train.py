@@ -4,7 +4,7 @@ Reference order: x.to(device) -> model(x) -> loss -> optimizer.ze
 -> optimizer.step() -> scheduler.step().  Here the whole step — dropout-seed advance, forward plan,
 fused loss forward+backward, backward plan, one flat gradient all-reduce, one fused Adam over the flat
 parameter buffer — is issued through the C-ABI on one stream and, on a single GPU, captured once into
-a CUDA graph and replayed (≈400 kernel launches per step would otherwise be CPU-launch bound).
+a CUDA graph and replayed (812 kernel launches per step for seist_m_dpk would otherwise be CPU-launch bound).
 The per-step host syncs of the reference (`.item()`, barrier; train.py:124-135) are not on this path:
 `step()` returns the loss as a device scalar.
 """
