@@ -96,6 +96,34 @@ def test_plan_compiler_end_to_end_vs_reference_golden():
         assert (sd[k].float() - b.float()).abs().max().item() <= 1e-3 * (b.float().abs().max().item() + 1e-3), k
 
 
+def test_plan_compiler_regression_head_vs_reference_golden():
+    """Same as above for the regression family (seist_m_emg: HEADVEC ops, scaled sigmoid, Huber loss)."""
+    g = torch.load(os.path.join(GOLD, "seist_m_emg.pt"))
+    m = create_model("seist_m_emg", in_channels=3, in_samples=8192)
+    m.load_state_dict(g["state_dict"], strict=True)
+    m.set_drop_rates(**ZERO)
+    x = g["x"]
+    flat = P.FlatState(m, torch.device("cpu"))
+    pl = P.PlanBuilder(m, flat, x.shape[0], 8192, training=False).build()
+    P.allocate(pl, False)
+    y = Interp(pl).run_fwd(x)
+    y = y if y.dim() == 2 else y[:, :, 0]
+    assert (y - g["y_eval"]).abs().max().item() < 1e-4 * max(1.0, g["y_eval"].abs().max().item())
+    pl = P.PlanBuilder(m, flat, x.shape[0], 8192, training=True).build()
+    P.allocate(pl, True)
+    it = Interp(pl)
+    y = it.run_fwd(x).clone()
+    y2 = y if y.dim() == 2 else y[:, :, 0]
+    assert (y2 - g["y_train"]).abs().max().item() < 1e-4 * max(1.0, g["y_train"].abs().max().item())
+    p = y2.clone().requires_grad_(True)
+    R.huber_loss(p, g["target"]).backward()
+    it.run_bwd(p.grad.reshape(y.shape))
+    gmax = max(v.abs().max().item() for v in g["grads"].values())
+    for k, ref in g["grads"].items():
+        err = (flat.grad_view(k) - ref).abs().max().item()
+        assert err <= 1e-3 * ref.abs().max().item() + 1e-6 * gmax, (k, err)
+
+
 def test_grad_combine_plan_equals_default_plan(monkeypatch):
     """GRAD_COMBINE (opt-in, SEIST_COMBINE_CIN): the compiler marks the wide 1x1 convs, emits the in-place BN
     backward before their three backward ops and re-points those ops at the combined gradient; executed by the
