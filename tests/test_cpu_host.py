@@ -124,6 +124,37 @@ def test_plan_compiler_regression_head_vs_reference_golden():
         assert err <= 1e-3 * ref.abs().max().item() + 1e-6 * gmax, (k, err)
 
 
+@pytest.mark.parametrize("name,L", [("seist_s_pmp", 2048), ("seist_l_dpk", 1024)])
+def test_plan_compiler_vs_oracle_random_cotangent(name, L):
+    """Families without a golden fixture (classification head with softmax; the L preset with 4-branch MSMC and
+    two MPTL blocks): random non-degenerate parameters, train mode, arbitrary output cotangent - the interpreter
+    must reproduce the pinned oracle's outputs, parameter gradients and running statistics."""
+    from harness import randomize
+    torch.manual_seed(0)
+    m = randomize(create_model(name, in_channels=3, in_samples=L), seed=7)
+    m.set_drop_rates(**ZERO)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x, _ = R.synth_waveforms(3, L, seed=2)
+    sd_g = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+            for k, v in sd.items()}
+    y_ref, _ = R.forward(sd_g, x, R.spec_for(name), training=True)
+    dy = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(5)) / y_ref.numel()
+    y_ref.backward(dy)
+    flat = P.FlatState(m, torch.device("cpu"))
+    pl = P.PlanBuilder(m, flat, 3, L, training=True).build()
+    P.allocate(pl, True)
+    it = Interp(pl)
+    y = it.run_fwd(x).clone()
+    y2 = y.reshape(y_ref.shape)
+    assert (y2 - y_ref.detach()).abs().max().item() <= 1e-4 * max(1e-3, y_ref.abs().max().item())
+    it.run_bwd(dy.reshape(y.shape))
+    grads = {k: sd_g[k].grad for k, _ in m.named_parameters()}
+    gmax = max(v.abs().max().item() for v in grads.values())
+    for k, ref in grads.items():
+        err = (flat.grad_view(k) - ref).abs().max().item()
+        assert err <= 1e-3 * ref.abs().max().item() + 1e-5 * gmax, (k, err)
+
+
 def test_grad_combine_plan_equals_default_plan(monkeypatch):
     """GRAD_COMBINE (opt-in, SEIST_COMBINE_CIN): the compiler marks the wide 1x1 convs, emits the in-place BN
     backward before their three backward ops and re-points those ops at the combined gradient; executed by the
