@@ -124,11 +124,14 @@ def test_plan_compiler_regression_head_vs_reference_golden():
         assert err <= 1e-3 * ref.abs().max().item() + 1e-6 * gmax, (k, err)
 
 
-@pytest.mark.parametrize("name,L", [("seist_s_pmp", 2048), ("seist_l_dpk", 1024)])
+ALL_VARIANTS = [f"seist_{size}_{task}" for size in "sml" for task in ("dpk", "pmp", "emg", "baz", "dis")]
+
+
+@pytest.mark.parametrize("name,L", [(n, 2048 if n == "seist_s_pmp" else 1024) for n in ALL_VARIANTS])
 def test_plan_compiler_vs_oracle_random_cotangent(name, L):
-    """Families without a golden fixture (classification head with softmax; the L preset with 4-branch MSMC and
-    two MPTL blocks): random non-degenerate parameters, train mode, arbitrary output cotangent - the interpreter
-    must reproduce the pinned oracle's outputs, parameter gradients and running statistics."""
+    """All 15 registered variants (detection/picking, classification with softmax, the three regression heads; S, M
+    and the L preset with 4-branch MSMC and two MPTL blocks): random non-degenerate parameters, train mode,
+    arbitrary output cotangent - the interpreter must reproduce the pinned oracle's outputs and parameter gradients."""
     from harness import randomize
     torch.manual_seed(0)
     m = randomize(create_model(name, in_channels=3, in_samples=L), seed=7)
