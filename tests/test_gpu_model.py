@@ -208,7 +208,9 @@ def test_full_size_batch_properties():
         return (after - 0.9 * sd0[key].cuda()) / 0.1      # momentum 0.1 (reference default): recover the batch mean
 
     mu_full, mu_a, mu_b = stem_mean(x), stem_mean(x[:N // 2].contiguous()), stem_mean(x[N // 2:].contiguous())
-    assert (mu_full - 0.5 * (mu_a + mu_b)).abs().max().item() <= 1e-5 * (mu_full.abs().max().item() + 1e-3)
+    # recovering the batch mean from the momentum update amplifies the fp32 rounding of running_mean 10x
+    tol = 1e-5 * (mu_full.abs().max().item() + 1e-3) + 2e-6 * (sd0[key].abs().max().item() + 1e-3)
+    assert (mu_full - 0.5 * (mu_a + mu_b)).abs().max().item() <= tol
 
 
 @pytest.mark.gpu
