@@ -58,6 +58,9 @@ int launch_convk_fwd(const SeistOp& op, cudaStream_t s);
 int launch_convk_bwd_data(const SeistOp& op, cudaStream_t s);
 int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s);
 int launch_stem_compose(const SeistOp& op, bool fwd, cudaStream_t s);
+bool tcconv_eligible(const SeistOp& op, int mode);
+int launch_tcconv(const SeistOp& op, int mode, cudaStream_t s, int sm_count);
+int tcconv_error_flag();
 
 // tensor-core (tcgen05) paths (pw_tc.cu forward, bww_tc.cu weight gradient): validated against the interpreter
 // (tests/test_gpu_ops.py::test_tcgen05_kernels_match_interpreter) but, since the SIMT kernels moved to FFMA2 and
@@ -88,6 +91,23 @@ static bool use_tc(const SeistOp& op) {
   return (gelu && op.Cin >= 32 && op.Cout >= 16) || (op.Cin >= 64 && op.Cout >= 32);
 }
 
+// warp-specialised tcgen05 convolution engine (tcconv.cu): default for every eligible forward / data-gradient conv;
+// SEIST_TCC=0 disables it (A/B runs against the SIMT kernels), SEIST_TCC_K1=1 restricts it to 1x1 convolutions
+static int tcc_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("SEIST_TCC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
+static int tcc_k1_only() {
+  static int v = -1;
+  if (v < 0) { const char* e = std::getenv("SEIST_TCC_K1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
+static bool use_tcc(const SeistOp& op, int mode) {
+  if (!tcc_mode() || (tcc_k1_only() && op.k != 1)) return false;
+  return tcconv_eligible(op, mode);
+}
+
 static int sm_count() {
   if (g_sm_count == 0) {
     int dev = 0;
@@ -110,8 +130,8 @@ static int validate_conv(const SeistOp& op) {
 
 static int run_one(const SeistOp& op, cudaStream_t s) {
   switch (op.kind) {
-    case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (use_tc(op)) return launch_pw_tc_fwd(op, s, sm_count()); if (pw_eligible(op)) return launch_pw_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
-    case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); if (v) return v; if (pw_eligible(op)) return launch_pw_bwd_data(op, s, sm_count()); return convk_bwd_data_eligible(op) ? launch_convk_bwd_data(op, s) : launch_conv_bwd_data(op, s); }
+    case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (use_tcc(op, 0)) return launch_tcconv(op, 0, s, sm_count()); if (use_tc(op)) return launch_pw_tc_fwd(op, s, sm_count()); if (pw_eligible(op)) return launch_pw_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
+    case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); if (v) return v; if (use_tcc(op, 1)) return launch_tcconv(op, 1, s, sm_count()); if (pw_eligible(op)) return launch_pw_bwd_data(op, s, sm_count()); return convk_bwd_data_eligible(op) ? launch_convk_bwd_data(op, s) : launch_conv_bwd_data(op, s); }
     case SEIST_OP_CONV_BWD_W: { int v = validate_conv(op); if (v) return v; if (tc_mode() == 1 && bww_tc_eligible(op)) return launch_bww_tc(op, s, sm_count()); /* validated; opt-in (SEIST_TC=1) until it beats the SIMT kernel */ if (bwwk_mode() && bwwk_eligible(op)) return launch_bwwk(op, s, sm_count()); return bww_eligible(op) ? launch_bww_any(op, s, sm_count()) : launch_conv_bwd_w(op, s, sm_count()); }
     case SEIST_OP_RES_BWD: return (op.L_out & 3) ? launch_res_bwd(op, s) : launch_res_bwd4(op, s, sm_count());
     case SEIST_OP_ATT_FWD: return launch_att_fwd(op, s);
@@ -146,7 +166,7 @@ uint64_t seist_sizeof_op(void) { return sizeof(SeistOp); }
 uint64_t seist_sizeof_bn(void) { return sizeof(SeistBN); }
 const char* seist_last_error(void) { return seist::g_err; }
 uint64_t seist_launch_count(void) { return seist::g_launches.load(); }
-int seist_tc_error_flag(void) { return seist::pw_tc_error_flag() | seist::bww_tc_error_flag(); }
+int seist_tc_error_flag(void) { return seist::pw_tc_error_flag() | seist::bww_tc_error_flag() | seist::tcconv_error_flag(); }
 
 static std::vector<cudaEvent_t> g_events;
 static cudaEvent_t event_at(size_t i) {

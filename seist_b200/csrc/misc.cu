@@ -334,9 +334,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    const float* __restrict__ lr_p, const float* __restrict__ step_p,
                                                    float b1, float b2, float eps, float wd, int decoupled,
                                                    float gscale) {
-  const float lr = *lr_p, step = *step_p;
-  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
-  const float step_size = lr / bc1, rbc2 = rsqrtf(bc2);
+  // bias corrections in double like torch.optim.Adam (python floats): fp32 powf is ~3e-5 off at small step counts
+  const float lr = *lr_p;
+  const double step = (double)*step_p;
+  const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+  const float step_size = (float)((double)lr / bc1), rbc2 = (float)(1.0 / sqrt(bc2));
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float pi = p[i], gi = g[i] * gscale;
     if (wd != 0.f) {

@@ -25,19 +25,22 @@ def _stream_ptr() -> int:
 
 
 class _PlanFn(torch.autograd.Function):
-    """x -> y through the forward plan; backward runs the backward plan.  Parameter gradients are a
-    side effect (views of Engine.flat.G attached to `.grad`); `trigger` only keeps the node alive."""
+    """(x, *parameters) -> y through the forward plan; backward runs the backward plan and returns the parameter
+    gradients as ordinary autograd outputs (views of the engine's flat gradient buffer), so that
+    `loss.backward()` accumulates into `.grad`, `DistributedDataParallel`'s reducer hooks fire
+    (reference training/train.py:367-374) and `torch.optim` optimizers work unchanged."""
 
     @staticmethod
-    def forward(ctx, x, trigger, engine, plan):
+    def forward(ctx, x, engine, plan, *params):
         ctx.engine, ctx.plan = engine, plan
+        ctx.n_params = len(params)
         y = engine.run_forward(plan, x)
         return y.clone()
 
     @staticmethod
     def backward(ctx, dy):
-        ctx.engine.run_backward(ctx.plan, dy)
-        return None, None, None, None
+        grads = ctx.engine.run_backward(ctx.plan, dy)
+        return (None, None, None) + tuple(grads)
 
 
 class Engine:
@@ -45,10 +48,10 @@ class Engine:
         self.model = model
         self.flat: Optional[P.FlatState] = None
         self.plans: Dict[Tuple, P.Plan] = {}
-        self._trigger = None
         self.last_plan: Optional[P.Plan] = None
         self.overlap_bwd_w = True
         self._side = {}
+        self.seed_dev: Optional[torch.Tensor] = None     # ONE dropout step counter (device int64) shared by every plan
 
     # ---- lifecycle -------------------------------------------------------------------------------
     def invalidate(self, release_flat: bool = False):
@@ -61,8 +64,29 @@ class Engine:
         if self.flat is None or self.flat.device != device or not self.flat.valid():
             self.plans.clear()
             self.flat = P.FlatState(self.model, device)
-            self._trigger = torch.zeros(1, device=device, requires_grad=True)
+        if self.seed_dev is None or self.seed_dev.device != device:
+            old = None if self.seed_dev is None else int(self.seed_dev.item())
+            self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
+            self.seed_dev.fill_(self._initial_seed() if old is None else old)
         return self.flat
+
+    @staticmethod
+    def _initial_seed() -> int:
+        """Start of the dropout/DropPath step counter: follows torch.manual_seed() and differs per rank (the
+        reference's torch RNG streams do, training/train.py sets the seed per process); 62 bits, non-negative."""
+        rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+        z = (torch.initial_seed() * 0x9E3779B97F4A7C15 + (rank + 1) * 0xD1B54A32D192ED03) & ((1 << 64) - 1)
+        z ^= z >> 29
+        return z & ((1 << 62) - 1)
+
+    def dropout_seed(self) -> int:
+        """Current value of the dropout step counter (checkpoint it next to the optimizer state)."""
+        return 0 if self.seed_dev is None else int(self.seed_dev.item())
+
+    def set_dropout_seed(self, value: int):
+        if self.seed_dev is None:
+            raise RuntimeError("set_dropout_seed: the model has not been moved to a CUDA device yet")
+        self.seed_dev.fill_(int(value) & ((1 << 62) - 1))
 
     def sync_world(self) -> int:
         """World size over which BatchNorm statistics are shared (1 unless the BNs are SyncBatchNorm)."""
@@ -81,7 +105,7 @@ class Engine:
             if len(self.plans) >= 4:      # plans own large arenas; keep the cache small
                 self.plans.pop(next(iter(self.plans)))
             b = P.PlanBuilder(self.model, self.flat, N, L, training, world=world, need_backward=need_backward)
-            pl = P.finalize(b.build(), need_backward)
+            pl = P.finalize(b.build(), need_backward, step_seed=self.seed_dev)
             self.plans[key] = pl
         return pl
 
@@ -114,6 +138,9 @@ class Engine:
     def run_forward(self, plan: P.Plan, x: torch.Tensor) -> torch.Tensor:
         plan.x_in.x.copy_(x)
         if plan.training:
+            # a new set of dropout / DropPath masks for every training forward (the backward of this forward
+            # regenerates the same masks from the same counter value)
+            _lib.check(_lib.lib().seist_advance_seed(plan.step_seed.data_ptr(), _stream_ptr()), "seist_advance_seed")
             plan.stat.zero_()
         self._run_segments(plan, plan.c_fwd, plan.fwd_segments, plan.stat)
         if plan.training:
@@ -123,20 +150,19 @@ class Engine:
         return y if plan.y_out.L > 1 else y[:, :, 0]
 
     def run_backward(self, plan: P.Plan, dy: torch.Tensor):
+        """Run the backward plan for the output gradient `dy`; returns one gradient per parameter, in
+        `model.named_parameters()` order, as views of the flat gradient buffer (None for frozen parameters)."""
         flat = self.flat
-        p0 = flat.params[0]
-        fresh = p0.grad is None or p0.grad.data_ptr() != flat.G.data_ptr() + 4 * flat.pref[self._name0].off
-        if fresh:
-            flat.G.zero_()
+        flat.G.zero_()
         plan.gstat.zero_()
         plan.dWx.zero_()
         plan.y_out.dxd.copy_(dy.reshape(plan.y_out.dxd.shape))
         self._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat, side=True)
-        for name, p in self._named:
-            if p.grad is None:
-                p.grad = flat.grad_view(name)
-            elif p.grad.data_ptr() != flat.G.data_ptr() + 4 * flat.pref[name].off:
-                p.grad = p.grad + flat.grad_view(name)
+        # one copy of the 1.5 MB buffer: autograd may keep ("steal") the returned tensors as `.grad`, and the flat
+        # buffer is zeroed again by the next backward (gradient accumulation over several backward calls must add up)
+        out = flat.G.clone()
+        return [out[flat.pref[name].off:flat.pref[name].off + flat.pref[name].numel].view(flat.pref[name].shape)
+                if p.requires_grad else None for name, p in self._named]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         model = self.model
@@ -156,7 +182,7 @@ class Engine:
         plan = self.get_plan(N, L, training, need_bwd)
         with torch.cuda.device(x.device):
             if need_bwd:
-                return _PlanFn.apply(x, self._trigger, self, plan)
+                return _PlanFn.apply(x, self, plan, *[p for _, p in self._named])
             return self.run_forward(plan, x).clone()
 
     # ---- data-parallel helpers -------------------------------------------------------------------

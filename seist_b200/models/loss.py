@@ -72,7 +72,13 @@ class BCELoss(nn.Module):
             wvec = w.reshape(c).contiguous()
         else:
             raise ValueError(f"BCELoss weight of shape {tuple(w.shape)} does not broadcast over {c} channels")
-        return _BCEFn.apply(preds, targets, wvec, float(self._epsilon))
+        if preds.dim() != 3:
+            raise ValueError(f"BCELoss expects (N, C, L) predictions, got {tuple(preds.shape)}")
+        if targets.shape != preds.shape:          # the reference's torch expression would broadcast (or raise)
+            targets = targets.expand_as(preds)
+        # the kernels read raw fp32: cast labels of any other dtype / device first (never reinterpret)
+        targets = targets.to(device=preds.device, dtype=torch.float32)
+        return _BCEFn.apply(preds.float(), targets, wvec, float(self._epsilon))
 
 
 class _HuberFn(torch.autograd.Function):
@@ -113,7 +119,7 @@ class HuberLoss(nn.Module):
             raise RuntimeError("seist_b200.HuberLoss has no CPU path")
         if preds.shape != targets.shape:
             targets = targets.expand_as(preds)
-        return _HuberFn.apply(preds, targets.to(preds.dtype), self.delta)
+        return _HuberFn.apply(preds.float(), targets.to(device=preds.device, dtype=torch.float32), self.delta)
 
 
 # ---- losses of tasks outside the accelerated path (kept for the registry surface) ---------------

@@ -291,7 +291,10 @@ class SeismogramTransformer(nn.Module):
             self._engine = Engine(self)
         return self._engine
 
+    @torch._dynamo.disable
     def forward(self, x):
+        # `torch.compile(model)` (the reference's default, training/train.py:296-297) degrades to a graph break here:
+        # the forward is one opaque call into the C-ABI plan executor, there is nothing for Inductor to fuse
         if not x.is_cuda:
             raise RuntimeError("seist_b200 has no CPU path: the input must live on a CUDA (sm_100a) device")
         return self.engine().forward(x)

@@ -601,7 +601,7 @@ class PlanBuilder:
 # =================================================================================================
 # materialisation: allocate buffers, build ctypes descriptors
 # =================================================================================================
-def allocate(plan: Plan, with_backward: bool):
+def allocate(plan: Plan, with_backward: bool, step_seed: Optional[torch.Tensor] = None):
     dev = plan.device
     N = plan.N
     total = 0
@@ -641,7 +641,9 @@ def allocate(plan: Plan, with_backward: bool):
     plan.Wx = torch.zeros(max(getattr(plan, "wx_numel", 0), 4), dtype=torch.float32, device=dev)
     plan.dWx = torch.zeros_like(plan.Wx)
     plan.coef = torch.zeros(4 * nst, dtype=torch.float32, device=dev)   # [C][8] per BN entry
-    plan.step_seed = torch.zeros(1, dtype=torch.int64, device=dev)
+    # dropout step counter: the engine passes ONE device scalar shared by all its plans (a per-plan counter would
+    # restart whenever the batch shape changes)
+    plan.step_seed = step_seed if step_seed is not None else torch.zeros(1, dtype=torch.int64, device=dev)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> int:
@@ -764,9 +766,9 @@ def segments(ops: List[Op]) -> List[Tuple[int, int, List[int]]]:
     return segs
 
 
-def finalize(plan: Plan, with_backward: bool):
+def finalize(plan: Plan, with_backward: bool, step_seed: Optional[torch.Tensor] = None):
     """Allocate device memory and freeze the descriptors (device must be CUDA for execution)."""
-    allocate(plan, with_backward)
+    allocate(plan, with_backward, step_seed)
     tab = bn_table_struct(plan)
     raw = np.frombuffer(bytes(tab), dtype=np.uint8).copy()
     plan.bn_table_host = tab

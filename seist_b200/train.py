@@ -22,7 +22,8 @@ from .models.loss import BCELoss, HuberLoss
 
 
 def cyclic_lr(it: int, base_lr=8e-5, max_lr=1e-3, up=2000, down=3000, gamma: Optional[float] = None) -> float:
-    """torch CyclicLR(mode='exp_range', cycle_momentum=False) as configured by training/train.py:343-354."""
+    """Learning rate of torch CyclicLR(mode='exp_range', cycle_momentum=False) after `it` scheduler steps.
+    `gamma=None` means no decay; the reference always decays — build its schedule with `make_cyclic_lr`."""
     total = up + down
     ratio = up / total
     cycle = math.floor(1 + it / total)
@@ -30,6 +31,16 @@ def cyclic_lr(it: int, base_lr=8e-5, max_lr=1e-3, up=2000, down=3000, gamma: Opt
     sf = x / ratio if x <= ratio else (x - 1) / (ratio - 1)
     g = 1.0 if gamma is None else gamma ** it
     return base_lr + (max_lr - base_lr) * sf * g
+
+
+def make_cyclic_lr(steps: int, base_lr=8e-5, max_lr=1e-3, up=2000, down=3000):
+    """The reference's schedule (training/train.py:343-354): CyclicLR(base_lr, max_lr, step_size_up=up,
+    step_size_down=down, mode='exp_range', gamma=base_lr ** (1 / (2 * steps)), cycle_momentum=False), where
+    `steps` = epochs * len(train_loader).  Returns `it -> lr` for `Trainer(lr_schedule=...)`."""
+    if steps <= 0:
+        raise ValueError("make_cyclic_lr: steps must be positive")
+    gamma = float(base_lr) ** (1.0 / (2 * steps))
+    return lambda it: cyclic_lr(it, base_lr, max_lr, up, down, gamma)
 
 
 class Trainer:
@@ -70,7 +81,14 @@ class Trainer:
             self.step_t = torch.zeros(1, device=dev)
         self.lr_t = torch.full((1,), float(self.lr), device=dev)
         self.x_static = self.plan.x_in.x
-        self.t_static = torch.empty_like(target, device=dev)
+        if tuple(target.shape) != tuple(self.plan.y_out.x.shape if self.plan.y_out.L > 1 else self.plan.y_out.x[:, :, 0].shape):
+            raise ValueError(f"Trainer: target shape {tuple(target.shape)} does not match the model output "
+                             f"{tuple(self.plan.y_out.x.shape)}")
+        self.t_static = torch.empty(target.shape, dtype=torch.float32, device=dev)   # kernels read raw fp32
+        for a in ("_copy_stream", "_x_stage", "_t_stage", "_staged", "_consumed"):   # staging is per batch shape
+            if hasattr(self, a):
+                delattr(self, a)
+        self._has_staged = False
         self.loss_acc = torch.zeros(1, dtype=torch.float64, device=dev)
         self.loss_out = torch.zeros((), device=dev)
         self.gout = torch.ones(1, device=dev)
@@ -133,6 +151,9 @@ class Trainer:
         copy asynchronous (the reference moves batches with `.to(device)` inside the step instead)."""
         if self._shape is None:
             raise RuntimeError("prefetch() needs one step(x, target) first (it sizes the static buffers)")
+        if self._shape != (tuple(x.shape), tuple(target.shape)):
+            raise ValueError(f"prefetch(): batch of shape {tuple(x.shape)} / {tuple(target.shape)} does not match the "
+                             f"shapes the trainer was set up for {self._shape}; call step(x, target) to re-plan")
         if not hasattr(self, "_copy_stream"):
             dev = self.x_static.device
             self._copy_stream = torch.cuda.Stream(device=dev)
@@ -155,6 +176,8 @@ class Trainer:
         if x is None:
             if not getattr(self, "_has_staged", False):
                 raise RuntimeError("step() without arguments needs a prefetch()ed batch")
+            if not self.flat.valid():
+                raise RuntimeError("step(): the model's parameters were re-allocated (.to()/.cuda()); call step(x, target)")
             cur = torch.cuda.current_stream()
             cur.wait_event(self._staged)
             self.x_static.copy_(self._x_stage, non_blocking=True)      # device -> device, ~0.1 ms
@@ -204,4 +227,63 @@ class Trainer:
                 self._issue()
             self.launches_per_step = int(_lib.lib().seist_launch_count() - before)
         self.it += 1
-        return self.loss_out
+        return self.loss_out.clone()      # a fresh scalar per step (loss_out itself is overwritten by the next step)
+
+    # ---- checkpointing (reference models/_factory.py:59-87 stores optimizer.state_dict()) ----------------------
+    def state_dict(self) -> dict:
+        """A `torch.optim.Adam.state_dict()`-compatible dict (per-parameter `step`, `exp_avg`, `exp_avg_sq` in
+        `model.parameters()` order, one param group) plus the trainer's own counters (`seist_b200`: LR-schedule
+        position and dropout step counter), so `save_checkpoint(..., optimizer=trainer, ...)` round-trips."""
+        if self._shape is None:
+            raise RuntimeError("Trainer.state_dict(): run one step first (the Adam moments live on the device)")
+        state = {}
+        for i, (name, _) in enumerate(self.eng._named):
+            r = self.flat.pref[name]
+            state[i] = {"step": self.step_t[0].detach().clone().cpu(),
+                        "exp_avg": self.exp_avg[r.off:r.off + r.numel].view(r.shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[r.off:r.off + r.numel].view(r.shape).clone()}
+        group = {"lr": float(self.lr_t.item()), "betas": tuple(self.betas), "eps": self.eps,
+                 "weight_decay": self.weight_decay, "amsgrad": False, "maximize": False, "foreach": None,
+                 "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": bool(self.decoupled),
+                 "params": list(range(len(self.eng._named)))}
+        return {"state": state, "param_groups": [group],
+                "seist_b200": {"it": self.it, "dropout_seed": self.eng.dropout_seed()}}
+
+    def load_state_dict(self, sd: dict):
+        """Accepts `Trainer.state_dict()` or a plain `torch.optim.Adam.state_dict()` of the same model."""
+        if self._shape is None:
+            raise RuntimeError("Trainer.load_state_dict(): run (or set up) one step first")
+        named = self.eng._named
+        st = sd.get("state", {})
+        if len(st) not in (0, len(named)):
+            raise ValueError(f"optimizer state has {len(st)} entries, the model has {len(named)} parameters")
+        step = None
+        for i, (name, p) in enumerate(named):
+            e = st.get(i, st.get(str(i)))
+            if e is None:
+                continue
+            r = self.flat.pref[name]
+            if tuple(e["exp_avg"].shape) != tuple(r.shape):
+                raise ValueError(f"optimizer state of {name}: shape {tuple(e['exp_avg'].shape)} != {tuple(r.shape)}")
+            self.exp_avg[r.off:r.off + r.numel].copy_(e["exp_avg"].reshape(-1))
+            self.exp_avg_sq[r.off:r.off + r.numel].copy_(e["exp_avg_sq"].reshape(-1))
+            s_i = float(e["step"])
+            if step is not None and s_i != step:
+                raise ValueError("per-parameter Adam step counts differ; the fused update keeps one")
+            step = s_i
+        if step is not None:
+            self.step_t.fill_(step)
+        groups = sd.get("param_groups") or []
+        if groups:
+            g0 = groups[0]
+            self.lr = float(g0.get("lr", self.lr))
+            self.betas = tuple(g0.get("betas", self.betas))
+            self.eps = float(g0.get("eps", self.eps))
+            self.weight_decay = float(g0.get("weight_decay", self.weight_decay))
+            self.lr_t.fill_(self.lr)
+            self.graph = None                       # betas / eps / weight decay are baked into the captured launch
+        extra = sd.get("seist_b200")
+        if extra:
+            self.it = int(extra.get("it", self.it))
+            if "dropout_seed" in extra:
+                self.eng.set_dropout_seed(int(extra["dropout_seed"]))

@@ -96,6 +96,7 @@ def test_ops_match_interpreter(name, N, L, training, drops):
             if not err < TOL:
                 failures.append(f"bwd[{i}] {bc.name} {what}: rel {err:.3e} (max {ref:.3e})")
     assert not failures, "\n".join(failures[:30])
+    assert _lib.lib().seist_tc_error_flag() == 0, "a tensor-core kernel timed out on an mbarrier"
 
 
 @pytest.mark.gpu
