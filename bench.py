@@ -74,34 +74,68 @@ class ClockSampler:
                 "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
 
 
-def cpu_reference_step_rate(model_name, batch, length, steps, warmup, threads):
-    """The reference's CPU training step (training/train.py:87-111: forward, BCELoss, zero_grad, backward,
-    Adam.step) timed on the host cores through the pinned oracle port (oracle/seist_ref.py — the reference
-    checkout itself does not exist on the GPU box).  Dropout/DropPath are identity in the port."""
-    from oracle import seist_ref as R
-    from seist_b200.models import create_model
+def reference_step_rate(model_name, batch, length, steps, warmup, threads, device="cpu"):
+    """The reference's training step (training/train.py:87-111: forward, BCELoss / HuberLoss, zero_grad, backward,
+    Adam.step) timed on `device`.  kind "reference": the UNMODIFIED reference modules staged by oracle/build_ref.py
+    (models/seist.py + models/loss.py, default drop rates, torch's own kernels); kind "port": the pinned oracle
+    restatement (dropout identity) when the staged copy is absent.  Returns (waveforms/s, seconds, kind)."""
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    m = create_model(model_name, in_channels=3, in_samples=length)
-    sd = {k: (v.detach().clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k
-              else v.detach().clone()) for k, v in m.state_dict().items()}
-    params = [v for v in sd.values() if v.requires_grad]
-    opt = torch.optim.Adam(params, lr=8e-5)
-    spec = R.spec_for(model_name)
-    x, tgt = synthetic(batch, length, 99, spec.head if spec.head == "dpk" else "reg")
+    from oracle import build_ref
+    dev = torch.device(device)
+    head = "dpk" if model_name.endswith("dpk") else "reg"
+    x, tgt = synthetic(batch, length, 99, head)
+    x, tgt = x.to(dev), tgt.to(dev)
+
+    def sync():
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+
+    if build_ref.available():
+        M = build_ref.import_models()
+        model = M.create_model(model_name, in_channels=3, in_samples=length).to(dev).train()
+        loss_fn = (M.BCELoss(weight=[[0.5], [1], [1]]) if head == "dpk" else M.HuberLoss()).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=8e-5)
+        kind = "reference"
+
+        def step():
+            out = model(x)
+            loss = loss_fn(out, tgt)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+    else:
+        from oracle import seist_ref as R
+        from seist_b200.models import create_model
+        m = create_model(model_name, in_channels=3, in_samples=length)
+        sd = {k: (v.detach().clone().to(dev).requires_grad_(True) if v.dtype.is_floating_point and "running" not in k
+                  else v.detach().clone().to(dev)) for k, v in m.state_dict().items()}
+        opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=8e-5)
+        spec = R.spec_for(model_name)
+        kind = "port"
+
+        def step():
+            y, bufs = R.forward(sd, x, spec, training=True)
+            loss = R.bce_loss(y, tgt) if spec.head == "dpk" else R.huber_loss(y, tgt)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            for k, b in bufs.items():
+                sd[k] = b
     times = []
     for i in range(warmup + steps):
+        sync()
         t0 = time.perf_counter()
-        y, bufs = R.forward(sd, x, spec, training=True)
-        loss = R.bce_loss(y, tgt) if spec.head == "dpk" else R.huber_loss(y, tgt)
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-        for k, b in bufs.items():
-            sd[k] = b
+        step()
+        sync()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return batch * len(times) / sum(times), sum(times)
+    return batch * len(times) / sum(times), sum(times), kind
+
+
+def _kind_text(kind):
+    return ("unmodified reference modules staged in oracle/_ref, default drop rates" if kind == "reference"
+            else "oracle port of the reference step, dropout identity")
 
 
 def main():
@@ -144,13 +178,14 @@ def main():
             return
         steps = max(1, min(args.steps, 20))      # bounded sample: ~0.5 s per 32-waveform CPU step
         warm = max(1, min(args.warmup, 2))
-        rate, secs = cpu_reference_step_rate(args.model, args.cpu_batch, args.length, steps, warm, cores)
+        rate, secs, kind = reference_step_rate(args.model, args.cpu_batch, args.length, steps, warm, cores)
+        config["cpu_sample_batch"] = args.cpu_batch
+        config["workload"] += f"; this arm: the reference's CPU step on {cores} host threads, bounded sample of {args.cpu_batch} waveforms/step"
         line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"{steps} train steps of {args.cpu_batch} waveforms "
-                                           f"(oracle port of the reference step, dropout identity)"},
+                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                                 "sample": f"{steps} train steps of {args.cpu_batch} waveforms ({_kind_text(kind)})"},
                 "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return
@@ -236,15 +271,24 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = args.batch * world * args.steps / (ms_e2e / 1e3)
 
+    arena_gb = trainer.plan.arena_bytes / 1e9
+    launches_per_step, used_graph = trainer.launches_per_step, trainer.graph is not None
     # ---- dominant kernel roofline (rank 0) ---------------------------------------------------------
-    roofline, step_roofline, cpu_baseline = None, None, None
+    roofline, step_roofline, cpu_baseline, reference_gpu = None, None, None, None
     if rank == 0:
         rows = time_ops(trainer.plan, reps=2)
         tot = sum(r["ms"] for r in rows)
         rows.sort(key=lambda r: -r["ms"])
-        top = rows[0]
-        ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
-        # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/dram_traffic.json:
+        # the dominant kernel FAMILY of the step: ops aggregated by (op kind, kernel template family), measured live
+        # (every op launched alone, CUDA events on the launching stream, L2-evicting write in between)
+        fams = {}
+        for r in rows:
+            f = fams.setdefault(r.get("family", str(r["kind"])), {"ms": 0.0, "bytes": 0, "flops": 0.0, "ops": 0})
+            f["ms"] += r["ms"]; f["bytes"] += r["bytes"]; f["flops"] += r.get("flops", 0.0); f["ops"] += 1
+        fam_name, fam = max(fams.items(), key=lambda kv: kv[1]["ms"])
+        ach = fam["bytes"] / (fam["ms"] * 1e-3) / 1e9
+        top = max((r for r in rows if r.get("family", str(r["kind"])) == fam_name), key=lambda r: r["ms"])
+        # DRAM traffic of the family's largest op from the committed `ncu --set full` capture (profiles/dram_traffic.json:
         # dram__bytes_read.sum + dram__bytes_write.sum per launch at this batch size), null if not captured
         traffic = None
         try:
@@ -254,9 +298,20 @@ def main():
                 traffic = ent["dram_bytes"]
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": traffic, "ms": top["ms"], "algorithmic_bytes": top["bytes"],
-                    "share_of_step": top["ms"] / tot, "peak_source": peak_src}
+        tensor_pct = None
+        try:
+            tp = json.load(open(os.path.join(ROOT, "profiles", "tensor_pipe.json")))
+            tensor_pct = tp.get("families", {}).get(fam_name)
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": fam_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": traffic, "traffic_op": top["name"], "ms": fam["ms"],
+                    "algorithmic_bytes": fam["bytes"], "ops": fam["ops"], "share_of_step": fam["ms"] / tot,
+                    "tflops": fam["flops"] / (fam["ms"] * 1e-3) / 1e12, "tensor_pipe_pct": tensor_pct,
+                    "peak_source": peak_src,
+                    "families": {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4),
+                                     "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1), "ops": v["ops"]}
+                                 for k, v in sorted(fams.items(), key=lambda kv: -kv[1]["ms"])}}
         if args.op_times:
             os.makedirs(os.path.dirname(os.path.abspath(args.op_times)), exist_ok=True)
             json.dump({"total_ms_isolated": tot, "step_ms": ms / args.steps, "rows": rows}, open(args.op_times, "w"))
@@ -266,10 +321,21 @@ def main():
             step_roofline = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
                              "bytes_per_waveform": bpw, "model": "6 accesses per BN-input element + I/O (SURVEY 8d)"}
         if world == 1 and not args.no_cpu_baseline:
-            rate, secs = cpu_reference_step_rate(args.model, args.cpu_batch, args.length, args.cpu_steps, 1, cores)
-            cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            rate, secs, kind = reference_step_rate(args.model, args.cpu_batch, args.length, args.cpu_steps, 1, cores)
+            cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
                             "sample": f"{args.cpu_steps} train steps of {args.cpu_batch} waveforms "
-                                      f"({secs:.1f} s; oracle port of the reference step, dropout identity)"}
+                                      f"({secs:.1f} s; {_kind_text(kind)})"}
+            # informational, same box: the reference's modules under stock PyTorch eager on this B200
+            try:
+                del trainer
+                torch.cuda.empty_cache()
+                gb = min(args.batch, 128)
+                grate, gsecs, gkind = reference_step_rate(args.model, gb, args.length, 6, 3, cores, device=f"cuda:{local_rank}")
+                reference_gpu = {"value": grate, "unit": UNIT, "kind": gkind, "batch": gb,
+                                 "how": "stock PyTorch eager (cuDNN/cuBLAS, TF32 convs allowed as by default), fp32, "
+                                        "same train step, 6 timed steps after 3 warm-up"}
+            except Exception as e:      # noqa: BLE001
+                reference_gpu = {"unavailable": repr(e)[:200]}
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -278,11 +344,13 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": (x_h.numel() + t_h.numel()) * 4, "d2h_bytes_per_step": 4,
+                        "d2h": "the step's loss only; the model outputs stay on the device (the reference's train() copies "
+                               "them to the host every step for its CPU metrics, training/train.py:141 - out of this path)",
                         "h2d": "pinned host batch copied every step on a copy stream, one step ahead (Trainer.prefetch)"},
-                "gpu_launches": trainer.launches_per_step * args.steps,
-                "launches_per_step": trainer.launches_per_step, "cuda_graph": trainer.graph is not None,
+                "gpu_launches": launches_per_step * args.steps,
+                "launches_per_step": launches_per_step, "cuda_graph": used_graph,
                 "loss": loss_val, "clocks": clocks, "roofline": roofline, "step_roofline": step_roofline,
-                "cpu_baseline": cpu_baseline, "arena_gb": trainer.plan.arena_bytes / 1e9}
+                "cpu_baseline": cpu_baseline, "reference_gpu_eager": reference_gpu, "arena_gb": arena_gb}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIST_ABI_VERSION 7
+#define SEIST_ABI_VERSION 8
 #define SEIST_MAX_IN 3
 
 /* ---- BatchNorm table entry (nn.BatchNorm1d, models/seist.py:641) ---------------- */
@@ -38,6 +38,11 @@ typedef struct SeistBN {
   float* running_var;    /* [C] */
   double* stat;          /* [2C] sum(x), sum(x^2) of the BN input over (N, L)  (all ranks)       */
   double* gstat;         /* [2C] sum(du), sum(du * khat) of the gradient w.r.t. the BN output     */
+  double* stat_acc;      /* where the producers' epilogues ACCUMULATE this rank's part of `stat`: the same
+                            buffer on one GPU; under data parallelism (SyncBatchNorm, reference
+                            training/train.py:374) a buffer in NVLink-symmetric memory that the
+                            BN_PREPARE exchange sums over all ranks into `stat`                  */
+  double* gstat_acc;     /* idem for `gstat`                                                      */
   float* dgamma;         /* [C] */
   float* dbeta;          /* [C] */
   float* coef;           /* [C][8] per-channel coefficients written by the BN_PREPARE ops:
@@ -54,6 +59,23 @@ typedef struct SeistBN {
   float grad_scale;      /* multiplies dgamma/dbeta (1/world_size under data parallelism)         */
   int32_t pad_;
 } SeistBN;
+
+/* ---- data-parallel exchange over NVLink peer memory (replaces the per-BatchNorm NCCL calls of
+   torch.nn.SyncBatchNorm, torch/nn/modules/_functions.py, enabled by reference training/train.py:374,
+   and the DDP gradient all-reduce of training/train.py:369): every rank maps every other rank's
+   buffers (torch.distributed._symmetric_memory / cuMem fabric handles) and the kernels read them
+   directly; a per-lane epoch counter + release/acquire signal words form the barrier. -------------- */
+#define SEIST_MAX_WORLD 8
+#define SEIST_SIG_LANES 4   /* 0 forward statistics, 1 backward statistics, 2 gradients ready, 3 gradients consumed */
+typedef struct SeistComm {
+  int32_t world, rank;
+  double* stat_peer[SEIST_MAX_WORLD];   /* base of rank p's stat_acc buffer (peer-mapped device pointers)       */
+  double* gstat_peer[SEIST_MAX_WORLD];  /* base of rank p's gstat_acc buffer                                    */
+  float* grad_peer[SEIST_MAX_WORLD];    /* base of rank p's flat gradient buffer                                */
+  uint32_t* sig_peer[SEIST_MAX_WORLD];  /* rank p's signal pad: uint32 [SEIST_SIG_LANES][SEIST_MAX_WORLD]        */
+  uint32_t* epoch;                      /* local uint32 [SEIST_SIG_LANES]: exchanges issued per lane             */
+  int32_t* err;                         /* local: set to 1 when a peer wait timed out (bounded spin)            */
+} SeistComm;
 
 /* ---- operand view ---------------------------------------------------------------------------- */
 typedef struct SeistView {
@@ -158,6 +180,7 @@ typedef struct SeistOp {
   uint32_t seed_attn;
   int32_t pad0_;
 
+  const SeistComm* comm;        /* BN_PREPARE: device copy of the exchange descriptor, NULL on one GPU              */
   uint64_t zero_bytes;          /* SEIST_OP_ZERO */
   int32_t n_bn;                 /* BN_FINALIZE: entries in bn_table; BN_PREPARE: entries to prepare */
   int32_t bn_lo;                /* BN_PREPARE: first entry                                          */
@@ -170,6 +193,8 @@ uint64_t seist_sizeof_bn(void);
 const char* seist_last_error(void);
 /* number of kernel launches issued by this library since load (bench `gpu_launches`) */
 uint64_t seist_launch_count(void);
+/* name of the kernel family the dispatcher launches for `op` (e.g. "tcconv_fwd(tcgen05+TMA)"); static string */
+const char* seist_op_family(const SeistOp* op);
 /* 1 if a tensor-core kernel ever timed out waiting for its MMA completion barrier (bounded spin) */
 int seist_tc_error_flag(void);
 
@@ -195,10 +220,18 @@ int seist_huber_bwd(const float* preds, const float* targets, const float* gout,
                     float delta, float* dpreds, void* stream);
 
 /* torch.optim.Adam / AdamW (decoupled=1) single fused update over one flat buffer —
-   training/train.py:304-316.  lr and step are device scalars so the call is graph-replayable. */
+   training/train.py:304-316.  lr and step are device scalars so the call is graph-replayable; the
+   hyper-parameters are doubles like torch's python floats ((1 - beta) is formed in double). */
 int seist_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel,
-                    const float* lr, const float* step, float beta1, float beta2, float eps,
-                    float weight_decay, int32_t decoupled, float grad_scale, void* stream);
+                    const float* lr, const float* step, double beta1, double beta2, double eps,
+                    double weight_decay, int32_t decoupled, float grad_scale, void* stream);
+
+/* Gradient all-reduce (sum) over peer memory: out[i] = sum_p grad_peer[p][i], bracketed by two cross-rank
+   barriers (all gradients complete / all peers finished reading).  `comm` is the DEVICE copy; graph capturable. */
+int seist_comm_allreduce(const SeistComm* comm, int32_t world, float* out, int64_t numel, void* stream);
+/* cross-rank barrier on signal lane `lane` (tests / teardown) */
+int seist_comm_barrier(const SeistComm* comm, int32_t lane, void* stream);
+uint64_t seist_sizeof_comm(void);
 
 /* *seed += 1 (device scalar), keeps dropout streams distinct across graph replays */
 int seist_advance_seed(uint64_t* seed, void* stream);

@@ -8,19 +8,30 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libseist_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_IN = 3
+MAX_WORLD = 8
+SIG_LANES = 4
 
 
 class SeistBN(C.Structure):
     _fields_ = [
         ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
-        ("stat", C.c_void_p), ("gstat", C.c_void_p),
+        ("stat", C.c_void_p), ("gstat", C.c_void_p), ("stat_acc", C.c_void_p), ("gstat_acc", C.c_void_p),
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("coef", C.c_void_p),
         ("count", C.c_double),
         ("C", C.c_int32), ("chain", C.c_int32), ("use_batch", C.c_int32), ("is_chained", C.c_int32),
         ("eps", C.c_float), ("momentum", C.c_float), ("grad_scale", C.c_float), ("pad_", C.c_int32),
+    ]
+
+
+class SeistComm(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32),
+        ("stat_peer", C.c_void_p * MAX_WORLD), ("gstat_peer", C.c_void_p * MAX_WORLD),
+        ("grad_peer", C.c_void_p * MAX_WORLD), ("sig_peer", C.c_void_p * MAX_WORLD),
+        ("epoch", C.c_void_p), ("err", C.c_void_p),
     ]
 
 
@@ -48,6 +59,7 @@ class SeistOp(C.Structure):
         ("seed_elem", C.c_uint32), ("seed_path", C.c_uint32), ("seed_alpha", C.c_uint32),
         ("lse", C.c_void_p), ("delta", C.c_void_p),
         ("heads", C.c_int32), ("p_attn", C.c_float), ("seed_attn", C.c_uint32), ("pad0_", C.c_int32),
+        ("comm", C.c_void_p),
         ("zero_bytes", C.c_uint64), ("n_bn", C.c_int32), ("bn_lo", C.c_int32),
     ]
 
@@ -80,6 +92,8 @@ def lib():
     L.seist_last_error.restype = C.c_char_p
     L.seist_launch_count.restype = C.c_uint64
     L.seist_tc_error_flag.restype = C.c_int
+    L.seist_op_family.restype = C.c_char_p
+    L.seist_op_family.argtypes = [C.c_void_p]
     L.seist_plan_run.restype = C.c_int
     L.seist_plan_run.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     L.seist_plan_run2.restype = C.c_int
@@ -98,16 +112,23 @@ def lib():
                                   C.c_void_p]
     L.seist_adam_step.restype = C.c_int
     L.seist_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
-                                  C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                  C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
                                   C.c_float, C.c_void_p]
     L.seist_advance_seed.restype = C.c_int
     L.seist_advance_seed.argtypes = [C.c_void_p, C.c_void_p]
+    L.seist_sizeof_comm.restype = C.c_uint64
+    L.seist_comm_barrier.restype = C.c_int
+    L.seist_comm_barrier.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.seist_comm_allreduce.restype = C.c_int
+    L.seist_comm_allreduce.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
     if L.seist_abi_version() != ABI_VERSION:
         raise RuntimeError(f"seist_b200: ABI mismatch (lib {L.seist_abi_version()} != {ABI_VERSION})")
     if L.seist_sizeof_op() != C.sizeof(SeistOp) or L.seist_sizeof_bn() != C.sizeof(SeistBN):
         raise RuntimeError(
             f"seist_b200: struct layout mismatch op {L.seist_sizeof_op()} vs {C.sizeof(SeistOp)}, "
             f"bn {L.seist_sizeof_bn()} vs {C.sizeof(SeistBN)}")
+    if L.seist_sizeof_comm() != C.sizeof(SeistComm):
+        raise RuntimeError(f"seist_b200: SeistComm layout mismatch {L.seist_sizeof_comm()} vs {C.sizeof(SeistComm)}")
     _lib = L
     return L
 
@@ -115,7 +136,7 @@ def lib():
 EXPORTS = [
     "seist_abi_version", "seist_sizeof_op", "seist_sizeof_bn", "seist_last_error", "seist_launch_count",
     "seist_tc_error_flag", "seist_plan_run", "seist_plan_run2", "seist_bce_fwd", "seist_bce_bwd", "seist_huber_fwd", "seist_huber_bwd",
-    "seist_adam_step", "seist_advance_seed",
+    "seist_adam_step", "seist_advance_seed", "seist_comm_allreduce", "seist_comm_barrier", "seist_sizeof_comm", "seist_op_family",
 ]
 
 

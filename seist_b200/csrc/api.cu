@@ -91,21 +91,35 @@ static bool use_tc(const SeistOp& op) {
   return (gelu && op.Cin >= 32 && op.Cout >= 16) || (op.Cin >= 64 && op.Cout >= 32);
 }
 
-// warp-specialised tcgen05 convolution engine (tcconv.cu): default for every eligible forward / data-gradient conv;
-// SEIST_TCC=0 disables it (A/B runs against the SIMT kernels), SEIST_TCC_K1=1 restricts it to 1x1 convolutions
+// Tensor-core dispatch.  Measured on B200 at the bench configuration (profiles/r2_tc_vs_simt.txt): the warp-specialised
+// tcgen05 + TMA engine (tcconv.cu) beats the FFMA2 SIMT kernels where the contraction is wide or has taps to amortise
+// its per-element transform / epilogue cost (k-tap convolutions of the encoder stages at L <= 512, 1x1 convolutions with
+// >= 64 reduction channels), and loses on the narrow, long layers (stem, stage 0, head) where a SIMT thread does only
+// Cout/2 packed FMAs per input element.  SEIST_TCC: unset/"auto" = that rule, "1" = every eligible op (tests), "0" = never.
 static int tcc_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = std::getenv("SEIST_TCC"); v = (e && e[0] == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = std::getenv("SEIST_TCC"); v = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)); }
   return v;
 }
-static int tcc_k1_only() {
-  static int v = -1;
-  if (v < 0) { const char* e = std::getenv("SEIST_TCC_K1"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v;
+static bool tcc_auto(const SeistOp& op, int mode) {
+  const int Kd = mode == 0 ? op.Cin : op.Cout, Nd = mode == 0 ? op.Cout : op.Cin;
+  if (op.k > 1) return op.L_out <= 512 && Kd >= 8 && Nd >= 8;
+  if (mode == 0) return Kd >= 64 && Nd >= 48;
+  return Kd >= 96 && Nd >= 96;
 }
 static bool use_tcc(const SeistOp& op, int mode) {
-  if (!tcc_mode() || (tcc_k1_only() && op.k != 1)) return false;
-  return tcconv_eligible(op, mode);
+  const int m = tcc_mode();
+  if (m == 0 || !tcconv_eligible(op, mode)) return false;
+  return m == 1 || tcc_auto(op, mode);
+}
+// weight gradient of wide 1x1 convolutions on tcgen05 (bww_tc.cu): wins from 64 reduction channels up (L <= 256 there)
+static bool use_bww_tc(const SeistOp& op) {
+  if (!bww_tc_eligible(op)) return false;
+  const int m = tc_mode();
+  if (m == 1) return true;
+  const char* e = std::getenv("SEIST_BWW_TC");
+  if (e && e[0] == '0') return false;
+  return op.Cin >= 64 && op.Cout >= 32 && op.L_out <= 256;
 }
 
 static int sm_count() {
@@ -128,25 +142,87 @@ static int validate_conv(const SeistOp& op) {
   return 0;
 }
 
-static int run_one(const SeistOp& op, cudaStream_t s) {
+// which kernel family serves an op (also reported to the bench: `seist_op_family`)
+enum Family {
+  F_NONE = 0, F_TCCONV_FWD, F_TCCONV_BWD_DATA, F_PW_TC_FWD, F_PW_FWD, F_CONVK_FWD, F_CONV_FWD, F_PW_BWD_DATA, F_CONVK_BWD_DATA,
+  F_CONV_BWD_DATA, F_BWW_TC, F_BWWK, F_BWW, F_CONV_BWD_W, F_RES_BWD, F_RES_BWD4, F_ATT_FWD, F_ATT_BWD_Q, F_ATT_BWD_KV, F_HEADVEC_FWD,
+  F_HEADVEC_BWD, F_BN_FINALIZE_FWD, F_BN_FINALIZE_BWD, F_BN_PREPARE_FWD, F_BN_PREPARE_BWD, F_STEM_COMPOSE_FWD, F_STEM_COMPOSE_BWD,
+  F_GRAD_COMBINE, F_ZERO
+};
+static const char* kFamilyName[] = {
+  "none", "tcconv_fwd(tcgen05+TMA)", "tcconv_bwd_data(tcgen05+TMA)", "pw_tc_fwd(tcgen05)", "pw_fwd(simt)", "convk_fwd(simt)",
+  "conv_fwd(simt)", "pw_bwd_data(simt)", "convk_bwd_data(simt)", "conv_bwd_data(simt)", "bww_tc(tcgen05)", "bwwk(simt)", "bww(simt)",
+  "conv_bwd_w(simt)", "res_bwd", "res_bwd4", "att_fwd", "att_bwd_q", "att_bwd_kv", "headvec_fwd", "headvec_bwd", "bn_finalize_fwd",
+  "bn_finalize_bwd", "bn_prepare_fwd", "bn_prepare_bwd", "stem_compose_fwd", "stem_compose_bwd", "grad_combine", "zero"
+};
+
+static Family choose(const SeistOp& op) {
   switch (op.kind) {
-    case SEIST_OP_CONV_FWD: { int v = validate_conv(op); if (v) return v; if (use_tcc(op, 0)) return launch_tcconv(op, 0, s, sm_count()); if (use_tc(op)) return launch_pw_tc_fwd(op, s, sm_count()); if (pw_eligible(op)) return launch_pw_fwd(op, s, sm_count()); return convk_eligible(op) ? launch_convk_fwd(op, s) : launch_conv_fwd(op, s); }
-    case SEIST_OP_CONV_BWD_DATA: { int v = validate_conv(op); if (v) return v; if (use_tcc(op, 1)) return launch_tcconv(op, 1, s, sm_count()); if (pw_eligible(op)) return launch_pw_bwd_data(op, s, sm_count()); return convk_bwd_data_eligible(op) ? launch_convk_bwd_data(op, s) : launch_conv_bwd_data(op, s); }
-    case SEIST_OP_CONV_BWD_W: { int v = validate_conv(op); if (v) return v; if (tc_mode() == 1 && bww_tc_eligible(op)) return launch_bww_tc(op, s, sm_count()); /* validated; opt-in (SEIST_TC=1) until it beats the SIMT kernel */ if (bwwk_mode() && bwwk_eligible(op)) return launch_bwwk(op, s, sm_count()); return bww_eligible(op) ? launch_bww_any(op, s, sm_count()) : launch_conv_bwd_w(op, s, sm_count()); }
-    case SEIST_OP_RES_BWD: return (op.L_out & 3) ? launch_res_bwd(op, s) : launch_res_bwd4(op, s, sm_count());
-    case SEIST_OP_ATT_FWD: return launch_att_fwd(op, s);
-    case SEIST_OP_ATT_BWD_Q: return launch_att_bwd_q(op, s);
-    case SEIST_OP_ATT_BWD_KV: return launch_att_bwd_kv(op, s);
-    case SEIST_OP_HEADVEC_FWD: return launch_headvec_fwd(op, s);
-    case SEIST_OP_HEADVEC_BWD: return launch_headvec_bwd(op, s);
-    case SEIST_OP_BN_FINALIZE_FWD: return launch_bn_finalize(op, true, s);
-    case SEIST_OP_BN_FINALIZE_BWD: return launch_bn_finalize(op, false, s);
-    case SEIST_OP_BN_PREPARE_FWD: return launch_bn_prepare(op, true, s);
-    case SEIST_OP_BN_PREPARE_BWD: return launch_bn_prepare(op, false, s);
-    case SEIST_OP_STEM_COMPOSE_FWD: return launch_stem_compose(op, true, s);
-    case SEIST_OP_STEM_COMPOSE_BWD: return launch_stem_compose(op, false, s);
-    case SEIST_OP_GRAD_COMBINE: return launch_grad_combine(op, s, sm_count());
-    case SEIST_OP_ZERO: {
+    case SEIST_OP_CONV_FWD:
+      if (use_tcc(op, 0)) return F_TCCONV_FWD;
+      if (use_tc(op)) return F_PW_TC_FWD;
+      if (pw_eligible(op)) return F_PW_FWD;
+      return convk_eligible(op) ? F_CONVK_FWD : F_CONV_FWD;
+    case SEIST_OP_CONV_BWD_DATA:
+      if (use_tcc(op, 1)) return F_TCCONV_BWD_DATA;
+      if (pw_eligible(op)) return F_PW_BWD_DATA;
+      return convk_bwd_data_eligible(op) ? F_CONVK_BWD_DATA : F_CONV_BWD_DATA;
+    case SEIST_OP_CONV_BWD_W:
+      if (use_bww_tc(op)) return F_BWW_TC;
+      if (bwwk_mode() && bwwk_eligible(op)) return F_BWWK;
+      return bww_eligible(op) ? F_BWW : F_CONV_BWD_W;
+    case SEIST_OP_RES_BWD: return (op.L_out & 3) ? F_RES_BWD : F_RES_BWD4;
+    case SEIST_OP_ATT_FWD: return F_ATT_FWD;
+    case SEIST_OP_ATT_BWD_Q: return F_ATT_BWD_Q;
+    case SEIST_OP_ATT_BWD_KV: return F_ATT_BWD_KV;
+    case SEIST_OP_HEADVEC_FWD: return F_HEADVEC_FWD;
+    case SEIST_OP_HEADVEC_BWD: return F_HEADVEC_BWD;
+    case SEIST_OP_BN_FINALIZE_FWD: return F_BN_FINALIZE_FWD;
+    case SEIST_OP_BN_FINALIZE_BWD: return F_BN_FINALIZE_BWD;
+    case SEIST_OP_BN_PREPARE_FWD: return F_BN_PREPARE_FWD;
+    case SEIST_OP_BN_PREPARE_BWD: return F_BN_PREPARE_BWD;
+    case SEIST_OP_STEM_COMPOSE_FWD: return F_STEM_COMPOSE_FWD;
+    case SEIST_OP_STEM_COMPOSE_BWD: return F_STEM_COMPOSE_BWD;
+    case SEIST_OP_GRAD_COMBINE: return F_GRAD_COMBINE;
+    case SEIST_OP_ZERO: return F_ZERO;
+    default: return F_NONE;
+  }
+}
+
+static int run_one(const SeistOp& op, cudaStream_t s) {
+  if (op.kind == SEIST_OP_CONV_FWD || op.kind == SEIST_OP_CONV_BWD_DATA || op.kind == SEIST_OP_CONV_BWD_W) {
+    int v = validate_conv(op);
+    if (v) return v;
+  }
+  switch (choose(op)) {
+    case F_TCCONV_FWD: return launch_tcconv(op, 0, s, sm_count());
+    case F_TCCONV_BWD_DATA: return launch_tcconv(op, 1, s, sm_count());
+    case F_PW_TC_FWD: return launch_pw_tc_fwd(op, s, sm_count());
+    case F_PW_FWD: return launch_pw_fwd(op, s, sm_count());
+    case F_CONVK_FWD: return launch_convk_fwd(op, s);
+    case F_CONV_FWD: return launch_conv_fwd(op, s);
+    case F_PW_BWD_DATA: return launch_pw_bwd_data(op, s, sm_count());
+    case F_CONVK_BWD_DATA: return launch_convk_bwd_data(op, s);
+    case F_CONV_BWD_DATA: return launch_conv_bwd_data(op, s);
+    case F_BWW_TC: return launch_bww_tc(op, s, sm_count());
+    case F_BWWK: return launch_bwwk(op, s, sm_count());
+    case F_BWW: return launch_bww_any(op, s, sm_count());
+    case F_CONV_BWD_W: return launch_conv_bwd_w(op, s, sm_count());
+    case F_RES_BWD: return launch_res_bwd(op, s);
+    case F_RES_BWD4: return launch_res_bwd4(op, s, sm_count());
+    case F_ATT_FWD: return launch_att_fwd(op, s);
+    case F_ATT_BWD_Q: return launch_att_bwd_q(op, s);
+    case F_ATT_BWD_KV: return launch_att_bwd_kv(op, s);
+    case F_HEADVEC_FWD: return launch_headvec_fwd(op, s);
+    case F_HEADVEC_BWD: return launch_headvec_bwd(op, s);
+    case F_BN_FINALIZE_FWD: return launch_bn_finalize(op, true, s);
+    case F_BN_FINALIZE_BWD: return launch_bn_finalize(op, false, s);
+    case F_BN_PREPARE_FWD: return launch_bn_prepare(op, true, s);
+    case F_BN_PREPARE_BWD: return launch_bn_prepare(op, false, s);
+    case F_STEM_COMPOSE_FWD: return launch_stem_compose(op, true, s);
+    case F_STEM_COMPOSE_BWD: return launch_stem_compose(op, false, s);
+    case F_GRAD_COMBINE: return launch_grad_combine(op, s, sm_count());
+    case F_ZERO: {
       cudaError_t e = cudaMemsetAsync(op.out.x, 0, op.zero_bytes, s);
       if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
       return 0;
@@ -166,6 +242,7 @@ uint64_t seist_sizeof_op(void) { return sizeof(SeistOp); }
 uint64_t seist_sizeof_bn(void) { return sizeof(SeistBN); }
 const char* seist_last_error(void) { return seist::g_err; }
 uint64_t seist_launch_count(void) { return seist::g_launches.load(); }
+const char* seist_op_family(const SeistOp* op) { return op ? seist::kFamilyName[seist::choose(*op)] : "none"; }
 int seist_tc_error_flag(void) { return seist::pw_tc_error_flag() | seist::bww_tc_error_flag() | seist::tcconv_error_flag(); }
 
 static std::vector<cudaEvent_t> g_events;

@@ -226,8 +226,8 @@ __device__ __forceinline__ void view_khat(const SeistOp& op, const SeistView& v,
 // deposit a per-channel pair of gstat partial sums (called by one lane per warp)
 __device__ __forceinline__ void gstat_add(const SeistOp& op, const SeistView& v, int c, float s1, float s2) {
   const SeistBN& e = op.bn_table[v.bn];
-  atomicAdd(&e.gstat[v.bn_c0 + c], (double)s1);
-  atomicAdd(&e.gstat[e.C + v.bn_c0 + c], (double)s2);
+  atomicAdd(&e.gstat_acc[v.bn_c0 + c], (double)s1);
+  atomicAdd(&e.gstat_acc[e.C + v.bn_c0 + c], (double)s2);
 }
 
 // drop factors of the epilogue: fac = delta(n) * D(n,co,l), alpha(n)

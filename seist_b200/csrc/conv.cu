@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(NT) conv_fwd_kernel(const __grid_constant__ Se
       s2 = warp_sum(s2);
       if (lane == 0) {
         const SeistBN& e = op.bn_table[op.out.bn];
-        atomicAdd(&e.stat[op.out.bn_c0 + co], (double)s1);
-        atomicAdd(&e.stat[e.C + op.out.bn_c0 + co], (double)s2);
+        atomicAdd(&e.stat_acc[op.out.bn_c0 + co], (double)s1);
+        atomicAdd(&e.stat_acc[e.C + op.out.bn_c0 + co], (double)s2);
       }
     }
   }

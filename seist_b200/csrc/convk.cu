@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_fwd_kernel(const __grid_consta
       const int co = co_base + w0 * 8 + (i >> 1);
       if (co < co_end) {
         const SeistBN& e = op.bn_table[op.out.bn];
-        atomicAdd(&e.stat[(i & 1) * e.C + op.out.bn_c0 + co], (double)s);
+        atomicAdd(&e.stat_acc[(i & 1) * e.C + op.out.bn_c0 + co], (double)s);
       }
     }
   }
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_c
       const SeistView& v = op.in[vi];
       if (v.g != nullptr && v.bn >= 0) {
         const SeistBN& e = op.bn_table[v.bn];
-        atomicAdd(&e.gstat[(i & 1) * e.C + v.bn_c0 + cv], (double)s);
+        atomicAdd(&e.gstat_acc[(i & 1) * e.C + v.bn_c0 + cv], (double)s);
       }
     }
   }

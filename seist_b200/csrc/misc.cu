@@ -191,8 +191,10 @@ __global__ void bn_prepare_bwd_kernel(const SeistBN* tab, int bn_lo) {
     bn_bwd_coef(tab, bn, c, k[4], k[5], k[6]);
   }
 }
+int launch_bn_prepare_xchg(const SeistOp& op, bool fwd, cudaStream_t s);
 int launch_bn_prepare(const SeistOp& op, bool fwd, cudaStream_t s) {
   if (op.n_bn <= 0) return 0;
+  if (op.comm != nullptr) return launch_bn_prepare_xchg(op, fwd, s);     // data parallel: statistic sum over peer memory fused in
   if (fwd) bn_prepare_fwd_kernel<<<op.n_bn, 64, 0, s>>>(op.bn_table, op.bn_lo);
   else bn_prepare_bwd_kernel<<<op.n_bn, 64, 0, s>>>(op.bn_table, op.bn_lo);
   note_launch();
@@ -329,23 +331,26 @@ static int ew_grid(int64_t total) {
 // ================================================================================================
 // Adam
 // ================================================================================================
+// torch.optim.Adam's arithmetic: hyper-parameters are python doubles there, so (1 - beta) and the bias corrections are
+// formed in double before rounding to fp32 (1.f - 0.999f is 1.3e-5 away from float(1 - 0.999))
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                    const float* __restrict__ lr_p, const float* __restrict__ step_p,
-                                                   float b1, float b2, float eps, float wd, int decoupled,
+                                                   double b1d, double b2d, double epsd, double wdd, int decoupled,
                                                    float gscale) {
-  // bias corrections in double like torch.optim.Adam (python floats): fp32 powf is ~3e-5 off at small step counts
   const float lr = *lr_p;
   const double step = (double)*step_p;
-  const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+  const double bc1 = 1.0 - pow(b1d, step), bc2 = 1.0 - pow(b2d, step);
   const float step_size = (float)((double)lr / bc1), rbc2 = (float)(1.0 / sqrt(bc2));
+  const float b1 = (float)b1d, b2 = (float)b2d, omb1 = (float)(1.0 - b1d), omb2 = (float)(1.0 - b2d);
+  const float eps = (float)epsd, wd = (float)wdd, decay = (float)(1.0 - (double)lr * wdd);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float pi = p[i], gi = g[i] * gscale;
-    if (wd != 0.f) {
-      if (decoupled) pi *= 1.f - lr * wd; else gi = fmaf(wd, pi, gi);
+    if (wdd != 0.0) {
+      if (decoupled) pi *= decay; else gi = fmaf(wd, pi, gi);
     }
-    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
-    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    const float mi = fmaf(b1, m[i], omb1 * gi);
+    const float vi = fmaf(b2, v[i], omb2 * gi * gi);
     m[i] = mi;
     v[i] = vi;
     p[i] = pi - step_size * mi / (sqrtf(vi) * rbc2 + eps);
@@ -407,7 +412,7 @@ int seist_huber_bwd(const float* preds, const float* targets, const float* gout,
 }
 
 int seist_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t numel,
-                    const float* lr, const float* step, float beta1, float beta2, float eps, float weight_decay,
+                    const float* lr, const float* step, double beta1, double beta2, double eps, double weight_decay,
                     int32_t decoupled, float grad_scale, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (numel <= 0) return -1;

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
       const int co = co_base + (i >> 1);
       if (co < op.Cout) {
         const SeistBN& e = op.bn_table[op.out.bn];
-        atomicAdd(&e.stat[(i & 1) * e.C + op.out.bn_c0 + co], (double)s);
+        atomicAdd(&e.stat_acc[(i & 1) * e.C + op.out.bn_c0 + co], (double)s);
       }
     });
   }
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
     const PwChan& c = ch_s[i >> 1];
     if (c.g != nullptr && c.bn >= 0) {
       const SeistBN& e = op.bn_table[c.bn];
-      atomicAdd(&e.gstat[(i & 1) * e.C + c.bnc], (double)s);
+      atomicAdd(&e.gstat_acc[(i & 1) * e.C + c.bnc], (double)s);
     }
   });
 }
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(PW_NT) res_bwd4_kernel(const __grid_constant__
     const bool w = (i >> 1) == 0 ? wa : wb;
     if (w && v.bn >= 0) {
       const SeistBN& e = op.bn_table[v.bn];
-      atomicAdd(&e.gstat[(i & 1) * e.C + v.bn_c0 + co], (double)s);
+      atomicAdd(&e.gstat_acc[(i & 1) * e.C + v.bn_c0 + co], (double)s);
     }
   });
 }

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(TC_NT) pw_tc_fwd_kernel(const __grid_constant_
     const SeistBN& e = op.bn_table[op.out.bn];
     for (int i = tid; i < 2 * Cout; i += TC_NT) {
       const float s = (red_s[i] + red_s[2 * Cout + i]) + (red_s[4 * Cout + i] + red_s[6 * Cout + i]);
-      atomicAdd(&e.stat[(i & 1) * e.C + op.out.bn_c0 + (i >> 1)], (double)s);
+      atomicAdd(&e.stat_acc[(i & 1) * e.C + op.out.bn_c0 + (i >> 1)], (double)s);
     }
   }
   __syncthreads();

@@ -11,14 +11,14 @@
 //   so the descriptor of tap t is just  start += 16*t  (LBO = pitch between channel quads, SBO = 128 between 8-row groups).
 //   No im2col copy, no weight expansion: k * ceil(K/8) MMAs of 128 x N x 8 per tile and precision pass.
 //
-// Warp roles (one persistent CTA per SM, 448 threads):
-//   warp 13      TMA producer: cp.async.bulk.tensor boxes {rows, 8 channels} of the raw fp32 operand tensors -> raw ring
+// Warp roles (one persistent CTA per SM, 576 threads):
+//   warp 17      TMA producer: cp.async.bulk.tensor boxes {rows, 8 channels} of the raw fp32 operand tensors -> raw ring
 //                (zero fill outside the tensor = the conv's zero padding of the raw rows; mbarrier complete_tx)
-//   warps 5..12  transform: raw ring -> BN-apply / GELU (forward) or BN-backward / dropout / sigmoid' (data gradient)
+//   warps 9..16  transform: raw ring -> BN-apply / GELU (forward) or BN-backward / dropout / sigmoid' (data gradient)
 //                -> exact hi + lo TF32 split -> panel ring (generic stores + fence.proxy.async)
-//   warp 4       MMA issuer: one elected thread, tcgen05.mma kind::tf32, 3 passes (hi*hi + lo*hi + hi*lo ~ fp32 products),
+//   warp 8       MMA issuer: one elected thread, tcgen05.mma kind::tf32, 3 passes (hi*hi + lo*hi + hi*lo ~ fp32 products),
 //                tcgen05.commit releases panel stages and publishes the accumulator
-//   warps 0..3   epilogue: tcgen05.ld from a double-buffered TMEM accumulator (lane = sample), bias / dropout /
+//   warps 0..7   epilogue (two groups of 4, one per TMEM accumulator buffer): tcgen05.ld (lane = sample), bias / dropout /
 //                residual views / BatchNorm statistics (forward) or GELU' / BN-backward sums / accumulate (data gradient),
 //                coalesced 128-byte stores; overlaps the MMAs of the next tile.
 #include <cuda.h>
@@ -28,7 +28,7 @@
 
 namespace seist {
 
-constexpr int TCC_EPI_WARPS = 4;
+constexpr int TCC_EPI_WARPS = 8;      // two groups of 4 (TMEM lane quadrant = warp % 4); group g drains accumulator buffer g
 constexpr int TCC_XF_WARPS = 8;
 constexpr int TCC_NT = 32 * (TCC_EPI_WARPS + 1 + TCC_XF_WARPS + 1);
 constexpr int TCC_M = 128;
@@ -110,14 +110,14 @@ __device__ __forceinline__ void tcc_tma3(uint32_t dst, const CUtensorMap* map, i
 // bounded wait: never hangs the GPU; a timeout raises the CTA's abort flag (every role then leaves its loop)
 __device__ __forceinline__ bool tcc_wait(uint32_t bar, uint32_t parity, volatile int* abort_s) {
   uint32_t done = 0;
-  for (int it = 0; it < (1 << 22); ++it) {
+  for (int it = 0; it < (1 << 18); ++it) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)      // suspend-time hint (ns): sleep in hardware, wake on completion
         : "memory");
     if (done) return true;
-    if ((it & 63) == 63 && *abort_s) return false;
+    if ((it & 15) == 15 && *abort_s) return false;
   }
   *abort_s = 1;
   return false;
@@ -126,8 +126,24 @@ __device__ __forceinline__ void tcc_split(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   lo = x - hi;
 }
-__device__ __noinline__ float tcc_gelu(float x) { return gelu_f(x); }
-__device__ __noinline__ float tcc_gelu_grad(float x) { return gelu_grad_f(x); }
+// erf by Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32 rounding level): 1 rcp + 1 ex2 + 7 fma instead of the
+// ~40 instructions of erff - the transform warps are issue-bound on GELU otherwise
+__device__ __forceinline__ float tcc_erf(float z) {
+  const float a = fabsf(z);
+  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = exp2f(-1.4426950408889634f * a * a);
+  return copysignf(fmaf(-p * t, e, 1.0f), z);
+}
+__device__ __forceinline__ float tcc_gelu(float x) { return 0.5f * x * (1.0f + tcc_erf(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float tcc_gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + tcc_erf(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * exp2f(-0.72134752044448170368f * x * x);
+  return fmaf(x, pdf, cdf);
+}
 
 // 16 values per lane -> every lane gets the warp-wide sum of value tcc_red_index(lane) (17 shuffles instead of 80)
 __device__ __forceinline__ float tcc_reduce16(float (&v)[16], int lane) {
@@ -179,7 +195,7 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
   unsigned char* a_s = base + g.off_a;
   unsigned char* b_s = base + g.off_b;
   TccK* tk_s = reinterpret_cast<TccK*>(base + g.off_tab_k);                 // [Kd_pad]
-  float* red_s = reinterpret_cast<float*>(base + g.off_red);               // [4 warps][2*Nd]
+  float* red_s = reinterpret_cast<float*>(base + g.off_red);               // [8 epilogue warps][2*Nd]
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + g.off_bar);
   uint64_t* raw_full = bars;
   uint64_t* raw_empty = raw_full + TCC_MAX_STAGES;
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
       tg_s[ci] = e;
     }
   }
-  for (int i = tid; i < 4 * 2 * Nd; i += TCC_NT) red_s[i] = 0.f;
+  for (int i = tid; i < TCC_EPI_WARPS * 2 * Nd; i += TCC_NT) red_s[i] = 0.f;
 
   // weights -> panel B[chunk][t][c/4][n][c%4] (hi, lo).  Resident: every chunk once; streamed: per chunk by the transform warps.
   const int colpitchB = g.N_pad * 16;
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&t_full[i])), "r"(1) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&t_empty[i])), "r"(TCC_EPI_WARPS) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(&t_empty[i])), "r"(4) : "memory");
     }
     *abort_s = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -338,14 +354,18 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
     }
   } else if (warp > TCC_EPI_WARPS) {
     // =========================== transform warps ===========================
+    // warp -> one channel quad q (its 4 coefficient rows stay in registers for the whole chunk) and every
+    // (8 / nq)-th 32-row block of the panel; lane = panel row
     const int xw = warp - (TCC_EPI_WARPS + 1);
     int rs = 0, as = 0;
     uint32_t rph = 0, aph = 0;
     const int nq = g.KC >> 2, nrb = g.Rp >> 5;
-    const int units = nq * nrb;
+    const int q = xw & (nq - 1);
+    const int rb0 = xw / nq, rbs = TCC_XF_WARPS / nq;
     const int colpitchA = g.Rp * 16;
     const uint32_t thr = drop_threshold(op.p_elem);
     const float keep_s = op.p_elem > 0.f ? 1.0f / (1.0f - op.p_elem) : 1.f;
+    const int raw_t = g.raw_tensor_bytes >> 2;
     for (int tile = blockIdx.x; tile < total && !*abort_s; tile += gridDim.x) {
       const int n = tile / tiles_per_n;
       const int p0 = (tile - n * tiles_per_n) * TCC_M - g.padA;
@@ -354,64 +374,76 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
       for (int ch = 0; ch < g.nchunks; ++ch) {
         if (!tcc_wait(s32(&raw_full[rs]), rph, abort_s)) break;
         if (!tcc_wait(s32(&a_empty[as]), aph ^ 1, abort_s)) break;
-        const float* raw = reinterpret_cast<const float*>(raw_s + (size_t)rs * g.n_raw * g.raw_tensor_bytes);
-        const int raw_t = g.raw_tensor_bytes >> 2;
-        unsigned char* a_hi = a_s + (size_t)as * g.a_stage;
+        const float* raw = reinterpret_cast<const float*>(raw_s + (size_t)rs * g.n_raw * g.raw_tensor_bytes) + 4 * q * g.Rbox;
+        unsigned char* a_hi = a_s + (size_t)as * g.a_stage + q * colpitchA;
         unsigned char* a_lo = a_hi + g.a_part;
-        for (int u = xw; u < units; u += TCC_XF_WARPS) {
-          const int q = u / nrb, rb = u - q * nrb;
-          const int r = rb * 32 + lane;
-          const int p = p0 + r;
-          const bool inb = (r < g.R) && p >= 0 && p < g.src_len;
-          float t[4];
-          if (MODE == 0) {
+        const int cbase = ch * g.KC + 4 * q;
+        TccK e[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int cl = 4 * q + j;
-              const TccK e = tk_s[ch * g.KC + cl];
-              float v = (r < g.Rbox) ? raw[cl * g.Rbox + r] : 0.f;
-              v = fmaf(e.a, v, e.b);
-              if (F_GELU && e.c != 0.f) v = tcc_gelu(v);
-              t[j] = (inb && ch * g.KC + cl < Kd) ? v : 0.f;
-            }
-          } else {
-            uint64_t hq = 0ull;
-            if (F_ELEM) {        // the 4 lanes of a sample quad share one hash per channel: each lane hashes ONE channel
-              const int ck = min(ch * g.KC + 4 * q + (lane & 3), Kd - 1);
-              hq = rng_u64(seed, op.seed_elem, (((uint64_t)n * op.Cout + ck) * (uint64_t)op.L_out + (uint64_t)(inb ? p : 0)) >> 2);
-            }
+        for (int j = 0; j < 4; ++j) e[j] = tk_s[cbase + j];
+        const int nvalid = Kd - cbase;          // channels of this quad that exist (<= 0: padded quad, all zero)
+        for (int rb = rb0; rb < nrb; rb += 2 * rbs) {
+          // two 32-row blocks per iteration: 8 independent element chains in flight (the warps are latency-, not
+          // throughput-bound otherwise), all shared-memory loads before the first store
+          float t[2][4];
+          int rrow[2];
+          bool act[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int cl = 4 * q + j;
-              const TccK e = tk_s[ch * g.KC + cl];
-              int slot = 0;
-              float dxd = 0.f, du = 0.f, x = 0.f;
-              const int ro = cl * g.Rbox + (r < g.Rbox ? r : 0);
-              if (g.has_dxd) { dxd = raw[slot * raw_t + ro]; ++slot; }
-              if (g.has_bn) { du = raw[slot * raw_t + ro]; ++slot; }
-              if (g.need_x) { x = raw[slot * raw_t + ro]; ++slot; }
-              float gv = dxd + fmaf(e.a, du, fmaf(e.b, x, e.c));
-              if (op.out_act == SEIST_OUT_SIGMOID) gv *= x * (1.f - x);
-              gv *= pfaf;
-              if (F_ELEM) {
-                const uint64_t hh = __shfl_sync(0xffffffffu, hq, (lane & ~3) | j);
-                gv *= (((uint32_t)(hh >> (16 * (p & 3))) & 0xFFFFu) >= thr) ? keep_s : 0.f;
+          for (int h = 0; h < 2; ++h) {
+            const int r = (rb + h * rbs) * 32 + lane;
+            rrow[h] = r;
+            act[h] = (rb + h * rbs) < nrb;
+            const int p = p0 + r;
+            const bool inb = act[h] && (r < g.R) && p >= 0 && p < g.src_len;
+            const int rr = (act[h] && r < g.Rbox) ? r : 0;
+            if (MODE == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float v = fmaf(e[j].a, raw[j * g.Rbox + rr], e[j].b);
+                if (F_GELU && e[j].c != 0.f) v = tcc_gelu(v);
+                t[h][j] = (inb && j < nvalid) ? v : 0.f;
               }
-              t[j] = (inb && ch * g.KC + cl < Kd) ? gv : 0.f;
+            } else {
+              uint64_t hq = 0ull;
+              if (F_ELEM) {        // the 4 lanes of a sample quad share one hash per channel: each lane hashes ONE channel
+                const int ck = min(cbase + (lane & 3), Kd - 1);
+                hq = rng_u64(seed, op.seed_elem, (((uint64_t)n * op.Cout + ck) * (uint64_t)op.L_out + (uint64_t)(inb ? p : 0)) >> 2);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int ro = j * g.Rbox + rr;
+                int slot = 0;
+                float dxd = 0.f, du = 0.f, x = 0.f;
+                if (g.has_dxd) { dxd = raw[ro]; ++slot; }
+                if (g.has_bn) { du = raw[slot * raw_t + ro]; ++slot; }
+                if (g.need_x) { x = raw[slot * raw_t + ro]; }
+                float gv = dxd + fmaf(e[j].a, du, fmaf(e[j].b, x, e[j].c));
+                if (op.out_act == SEIST_OUT_SIGMOID) gv *= x * (1.f - x);
+                gv *= pfaf;
+                if (F_ELEM) {
+                  const uint64_t hh = __shfl_sync(0xffffffffu, hq, (lane & ~3) | j);
+                  gv *= (((uint32_t)(hh >> (16 * (p & 3))) & 0xFFFFu) >= thr) ? keep_s : 0.f;
+                }
+                t[h][j] = (inb && j < nvalid) ? gv : 0.f;
+              }
             }
           }
-          if (r < g.Rp) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (!act[h]) continue;
             float4 hi, lo;
-            tcc_split(t[0], hi.x, lo.x);
-            tcc_split(t[1], hi.y, lo.y);
-            tcc_split(t[2], hi.z, lo.z);
-            tcc_split(t[3], hi.w, lo.w);
-            const int off = q * colpitchA + r * 16;
-            *reinterpret_cast<float4*>(a_hi + off) = hi;
-            if (g.passes > 1) *reinterpret_cast<float4*>(a_lo + off) = lo;
+            tcc_split(t[h][0], hi.x, lo.x);
+            tcc_split(t[h][1], hi.y, lo.y);
+            tcc_split(t[h][2], hi.z, lo.z);
+            tcc_split(t[h][3], hi.w, lo.w);
+            *reinterpret_cast<float4*>(a_hi + rrow[h] * 16) = hi;
+            if (g.passes > 1) *reinterpret_cast<float4*>(a_lo + rrow[h] * 16) = lo;
           }
         }
-        if (!g.b_resident) stage_b(ch, a_hi + 2 * g.a_part, a_hi + 2 * g.a_part + g.b_part, xw * 32 + lane, TCC_XF_WARPS * 32);
+        if (!g.b_resident) {
+          unsigned char* bst = a_s + (size_t)as * g.a_stage + 2 * g.a_part;
+          stage_b(ch, bst, bst + g.b_part, xw * 32 + lane, TCC_XF_WARPS * 32);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
@@ -472,74 +504,96 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
       if (!ok) break;
     }
   } else {
-    // =========================== epilogue warps (TMEM lanes 32*warp .. 32*warp+31) ===========================
+    // =========================== epilogue warps ===========================
+    // group eg = warp / 4 drains accumulator buffer eg (tiles it = eg, eg + 2, ...); TMEM lanes 32 * (warp % 4) ..
+    const int eg = warp >> 2, wq = warp & 3;
     const int L = g.dst_len;
     const bool stats = MODE == 0 ? ((op.out.bn >= 0) && op.bn_table[op.out.bn >= 0 ? op.out.bn : 0].use_batch) : true;
     const float* ep_s = reinterpret_cast<const float*>(base + g.off_tab_n);
     const TccTgt* tg_s = reinterpret_cast<const TccTgt*>(base + g.off_tab_n);
     const uint32_t thr = drop_threshold(op.p_elem);
     const float keep_s = op.p_elem > 0.f ? 1.0f / (1.0f - op.p_elem) : 1.f;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total && !*abort_s; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
+    float* my_red = red_s + warp * 2 * Nd;
+    const bool has_ra = MODE == 0 && op.res_a.C > 0, has_rb = MODE == 0 && op.res_b.C > 0;
+    const bool sig = op.out_act == SEIST_OUT_SIGMOID;
+    const size_t Ls = (size_t)L;
+    int it = eg;
+    for (int tile = blockIdx.x + eg * gridDim.x; tile < total && !*abort_s; tile += 2 * gridDim.x, it += 2) {
       const uint32_t tph = (uint32_t)(it >> 1) & 1u;
       const int n = tile / tiles_per_n;
-      const int l = (tile - n * tiles_per_n) * TCC_M + 32 * warp + lane;
+      const int l = (tile - n * tiles_per_n) * TCC_M + 32 * wq + lane;
       const bool ok = l < L;
-      if (!tcc_wait(s32(&t_full[acc]), tph, abort_s)) break;
+      const int ls = ok ? l : 0;
+      if (!tcc_wait(s32(&t_full[eg]), tph, abort_s)) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t trow = tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)(acc * g.N_pad);
+      const uint32_t trow = tmem_base + ((uint32_t)(32 * wq) << 16) + (uint32_t)(eg * g.N_pad);
       if (MODE == 0) {
         const float pf = path_factor(op, seed, n), af = alpha_factor(op, seed, n);
-        float* optr = op.out.x + ((size_t)n * op.out.Ct + op.out.c0) * (size_t)L + (ok ? l : 0);
-        const float* ra = op.res_a.C > 0 ? op.res_a.x + ((size_t)n * op.res_a.Ct + op.res_a.c0) * (size_t)L + (ok ? l : 0) : nullptr;
-        const float* rb = op.res_b.C > 0 ? op.res_b.x + ((size_t)n * op.res_b.Ct + op.res_b.c0) * (size_t)L + (ok ? l : 0) : nullptr;
+        float* optr = op.out.x + ((size_t)n * op.out.Ct + op.out.c0) * Ls + ls;
+        const float* ra = has_ra ? op.res_a.x + ((size_t)n * op.res_a.Ct + op.res_a.c0) * Ls + ls : nullptr;
+        const float* rb = has_rb ? op.res_b.x + ((size_t)n * op.res_b.Ct + op.res_b.c0) * Ls + ls : nullptr;
 #pragma unroll 1
         for (int c0 = 0; c0 < Nd; c0 += 16) {
           uint32_t rr[16];
           TCC_LD16(rr, trow + (uint32_t)c0);
-          float rav[16], rbv[16];
+          const int nv = min(16, Nd - c0);               // uniform
+          float val[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {          // all residual loads of the group before the first store
-            const int co = min(c0 + c, Nd - 1);
-            rav[c] = (ra && ok) ? __ldg(ra + (size_t)co * L) : 0.f;
-            rbv[c] = (rb && ok) ? __ldg(rb + (size_t)co * L) : 0.f;
-          }
-          uint64_t hq[4] = {0ull, 0ull, 0ull, 0ull};
+          for (int c = 0; c < 16; ++c) val[c] = (__uint_as_float(rr[c]) + ep_s[min(c0 + c, Nd - 1)]) * pf;
           if (F_ELEM) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int ck = min(c0 + 4 * q + (lane & 3), Nd - 1);
-              hq[q] = rng_u64(seed, op.seed_elem, (((uint64_t)n * Nd + ck) * (uint64_t)L + (uint64_t)(ok ? l : 0)) >> 2);
+            for (int qd = 0; qd < 4; ++qd) {
+              const int ck = min(c0 + 4 * qd + (lane & 3), Nd - 1);
+              const uint64_t hq = rng_u64(seed, op.seed_elem, (((uint64_t)n * Nd + ck) * (uint64_t)L + (uint64_t)ls) >> 2);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint64_t hh = __shfl_sync(0xffffffffu, hq, (lane & ~3) | j);
+                val[4 * qd + j] *= ((uint32_t)(hh >> (16 * (l & 3))) & 0xFFFFu) >= thr ? keep_s : 0.f;
+              }
             }
           }
-          float s1[16], s2[16];
+          if (has_ra) {
+            float rv[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) rv[c] = __ldg(ra + (size_t)min(c, nv - 1) * Ls);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) val[c] += fmaf(ep_s[Nd + min(c0 + c, Nd - 1)], rv[c], ep_s[2 * Nd + min(c0 + c, Nd - 1)]);
+            ra += 16 * Ls;
+          }
+          if (af != 1.f) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) val[c] *= af;
+          }
+          if (has_rb) {
+            float rv[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) rv[c] = __ldg(rb + (size_t)min(c, nv - 1) * Ls);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) val[c] += fmaf(ep_s[3 * Nd + min(c0 + c, Nd - 1)], rv[c], ep_s[4 * Nd + min(c0 + c, Nd - 1)]);
+            rb += 16 * Ls;
+          }
+          if (sig) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) val[c] = sigmoid_f(val[c]);
+          }
+          float* op_c = optr;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            const int co = c0 + c;
-            float val = 0.f, kf = 1.f;
-            if (F_ELEM) {
-              const uint64_t hh = __shfl_sync(0xffffffffu, hq[c >> 2], (lane & ~3) | (c & 3));
-              kf = ((uint32_t)(hh >> (16 * (l & 3))) & 0xFFFFu) >= thr ? keep_s : 0.f;
-            }
-            if (ok && co < Nd) {
-              val = (__uint_as_float(rr[c]) + ep_s[co]) * pf;
-              if (F_ELEM) val *= kf;
-              if (ra) val += fmaf(ep_s[Nd + co], rav[c], ep_s[2 * Nd + co]);
-              val *= af;
-              if (rb) val += fmaf(ep_s[3 * Nd + co], rbv[c], ep_s[4 * Nd + co]);
-              if (op.out_act == SEIST_OUT_SIGMOID) val = sigmoid_f(val);
-              optr[(size_t)co * L] = val;
-            }
-            s1[c] = val;
-            s2[c] = val * val;
+            const bool w = ok && c < nv;
+            if (w) *op_c = val[c];
+            val[c] = w ? val[c] : 0.f;
+            op_c += Ls;
           }
+          optr += 16 * Ls;
           if (stats) {
-            const float t1 = tcc_reduce16(s1, lane), t2 = tcc_reduce16(s2, lane);
+            float s2[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) s2[c] = val[c] * val[c];
+            const float t1 = tcc_reduce16(val, lane), t2 = tcc_reduce16(s2, lane);
             const int co = c0 + tcc_red_index(lane);
             if ((lane & 1) == 0 && co < Nd) {        // single writer per (warp, channel): deterministic
-              red_s[warp * 2 * Nd + 2 * co] += t1;
-              red_s[warp * 2 * Nd + 2 * co + 1] += t2;
+              my_red[2 * co] += t1;
+              my_red[2 * co + 1] += t2;
             }
           }
         }
@@ -553,7 +607,7 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
           for (int c = 0; c < 16; ++c) {
             const TccTgt& e = tg_s[min(c0 + c, Nd - 1)];
             const bool live = ok && (c0 + c < Nd) && e.g != nullptr;
-            const long long off = (long long)n * e.nstride + (ok ? l : 0);
+            const long long off = (long long)n * e.nstride + ls;
             xv[c] = (live && (e.bn >= 0 || (F_GELU && e.act == SEIST_ACT_GELU))) ? __ldg(e.x + off) : 0.f;
             ov[c] = (live && e.accum) ? e.g[off] : 0.f;
           }
@@ -572,14 +626,14 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
           const float t1 = tcc_reduce16(s1, lane), t2 = tcc_reduce16(s2, lane);
           const int ci = c0 + tcc_red_index(lane);
           if ((lane & 1) == 0 && ci < Nd) {
-            red_s[warp * 2 * Nd + 2 * ci] += t1;
-            red_s[warp * 2 * Nd + 2 * ci + 1] += t2;
+            my_red[2 * ci] += t1;
+            my_red[2 * ci + 1] += t2;
           }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) tcc_arrive(s32(&t_empty[acc]));
+      if (lane == 0) tcc_arrive(s32(&t_empty[eg]));
     }
   }
 
@@ -592,8 +646,9 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
     if (stats) {
       const SeistBN& e = op.bn_table[op.out.bn];
       for (int i = tid; i < 2 * Nd; i += TCC_NT) {
-        const float s = (red_s[i] + red_s[2 * Nd + i]) + (red_s[4 * Nd + i] + red_s[6 * Nd + i]);
-        atomicAdd(&e.stat[(i & 1) * e.C + op.out.bn_c0 + (i >> 1)], (double)s);
+        float s = 0.f;
+        for (int w = 0; w < TCC_EPI_WARPS; ++w) s += red_s[w * 2 * Nd + i];
+        atomicAdd(&e.stat_acc[(i & 1) * e.C + op.out.bn_c0 + (i >> 1)], (double)s);
       }
     }
   } else {
@@ -601,9 +656,10 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
     for (int i = tid; i < 2 * Nd; i += TCC_NT) {
       const TccTgt& t = tg_s[i >> 1];
       if (t.g != nullptr && t.bn >= 0) {
-        const float s = (red_s[i] + red_s[2 * Nd + i]) + (red_s[4 * Nd + i] + red_s[6 * Nd + i]);
+        float s = 0.f;
+        for (int w = 0; w < TCC_EPI_WARPS; ++w) s += red_s[w * 2 * Nd + i];
         const SeistBN& e = op.bn_table[t.bn];
-        atomicAdd(&e.gstat[(i & 1) * e.C + t.bnc], (double)s);
+        atomicAdd(&e.gstat_acc[(i & 1) * e.C + t.bnc], (double)s);
       }
     }
   }
@@ -700,11 +756,18 @@ static bool tcc_geometry(const SeistOp& op, int mode, TccGeom& g) {
   if (g.n_raw == 0) return false;
   const int tab_n = mode == 0 ? 5 * g.Nd * 4 : g.Nd * (int)sizeof(TccTgt);
   const int budget = 220 * 1024;
-  const int kcs[3] = {32, 16, 8};
+  // chunk width: fewest padded reduction channels first (the transform warps pay for padding), wider chunks second
+  int kcs[3] = {32, 16, 8};
+  {
+    const int k8 = (g.Kd + 7) & ~7;
+    auto waste = [&](int kc) { return ((k8 + kc - 1) / kc) * kc - k8; };
+    for (int i = 0; i < 3; ++i)
+      for (int j = i + 1; j < 3; ++j)
+        if (waste(kcs[j]) < waste(kcs[i])) { const int tmp = kcs[i]; kcs[i] = kcs[j]; kcs[j] = tmp; }
+  }
   for (int resident = 1; resident >= 0; --resident) {
     for (int ki = 0; ki < 3; ++ki) {
       const int KC = kcs[ki];
-      if (KC > 8 && KC >= 2 * ((g.Kd + 7) & ~7)) continue;        // do not pad tiny reductions to a wide chunk
       g.KC = KC;
       g.nchunks = (g.Kd + KC - 1) / KC;
       g.raw_tensor_bytes = KC * g.Rbox * 4;
@@ -715,7 +778,7 @@ static bool tcc_geometry(const SeistOp& op, int mode, TccGeom& g) {
       const int a_stage = 2 * g.a_part + (resident ? 0 : 2 * g.b_part);
       g.a_stage = a_stage;
       const int raw_stage = g.n_raw * g.raw_tensor_bytes;
-      const int fixed = b_bytes + g.nchunks * KC * (int)sizeof(TccK) + tab_n + 8 * g.Nd * 4 + (4 * TCC_MAX_STAGES + 4) * 8 + 64 + 256;
+      const int fixed = b_bytes + g.nchunks * KC * (int)sizeof(TccK) + tab_n + 16 * g.Nd * 4 + (4 * TCC_MAX_STAGES + 4) * 8 + 64 + 256;
       for (int st = 4; st >= 2; --st) {
         const int rst = st + 1 > TCC_MAX_STAGES ? TCC_MAX_STAGES : st + 1;
         const int tot = fixed + st * a_stage + rst * raw_stage;
@@ -730,7 +793,7 @@ static bool tcc_geometry(const SeistOp& op, int mode, TccGeom& g) {
           off = (off + 15) & ~15;
           g.off_tab_n = off; off += tab_n;
           off = (off + 15) & ~15;
-          g.off_red = off; off += 8 * g.Nd * 4;
+          g.off_red = off; off += 16 * g.Nd * 4;
           off = (off + 15) & ~15;
           g.off_bar = off; off += (4 * TCC_MAX_STAGES + 4) * 8 + 64;
           g.smem_bytes = off + 128;

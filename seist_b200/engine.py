@@ -52,6 +52,7 @@ class Engine:
         self.overlap_bwd_w = True
         self._side = {}
         self.seed_dev: Optional[torch.Tensor] = None     # ONE dropout step counter (device int64) shared by every plan
+        self.comm = None                                  # PeerComm (NVLink peer-memory exchange) under data parallelism
 
     # ---- lifecycle -------------------------------------------------------------------------------
     def invalidate(self, release_flat: bool = False):
@@ -64,6 +65,12 @@ class Engine:
         if self.flat is None or self.flat.device != device or not self.flat.valid():
             self.plans.clear()
             self.flat = P.FlatState(self.model, device)
+            if self.comm is not None:                 # the flat gradient buffer lives in symmetric memory
+                if self.comm.n_grad != self.flat.numel or self.comm.device != device:
+                    self.comm = None
+                else:
+                    self.flat.G = self.comm.grad
+                    self.flat.G.zero_()
         if self.seed_dev is None or self.seed_dev.device != device:
             old = None if self.seed_dev is None else int(self.seed_dev.item())
             self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
@@ -96,6 +103,20 @@ class Engine:
             return dist.get_world_size()
         return 1
 
+    def _ensure_comm(self, world: int):
+        """Peer-memory exchange for SyncBatchNorm statistics and gradients (comm.py); None on one GPU or with
+        SEIST_SYMM=0 (then the statistics are all-reduced with NCCL at the plan's sync points)."""
+        from .comm import PeerComm, symmetric_memory_enabled
+        if world <= 1 or not symmetric_memory_enabled():
+            return None
+        if self.comm is None:
+            n_stat = sum(2 * m.num_features for m in self.model.modules()
+                         if isinstance(m, nn.modules.batchnorm._BatchNorm))
+            self.comm = PeerComm(self.flat.device, world, dist.get_rank(), max(n_stat, 2), self.flat.numel)
+            self.flat.G = self.comm.grad
+            self.flat.G.zero_()
+        return self.comm
+
     def get_plan(self, N: int, L: int, training: bool, need_backward: bool) -> P.Plan:
         _lib.lib()   # fail loudly if the CUDA extension is missing
         world = self.sync_world() if training else 1
@@ -105,7 +126,8 @@ class Engine:
             if len(self.plans) >= 4:      # plans own large arenas; keep the cache small
                 self.plans.pop(next(iter(self.plans)))
             b = P.PlanBuilder(self.model, self.flat, N, L, training, world=world, need_backward=need_backward)
-            pl = P.finalize(b.build(), need_backward, step_seed=self.seed_dev)
+            comm = self._ensure_comm(world) if training else None
+            pl = P.finalize(b.build(), need_backward, step_seed=self.seed_dev, comm=comm)
             self.plans[key] = pl
         return pl
 
@@ -141,8 +163,10 @@ class Engine:
             # a new set of dropout / DropPath masks for every training forward (the backward of this forward
             # regenerates the same masks from the same counter value)
             _lib.check(_lib.lib().seist_advance_seed(plan.step_seed.data_ptr(), _stream_ptr()), "seist_advance_seed")
-            plan.stat.zero_()
-        self._run_segments(plan, plan.c_fwd, plan.fwd_segments, plan.stat)
+            if plan.comm is not None:
+                plan.comm.barrier()      # no peer is still reading last step's partial sums when they are cleared
+            plan.stat_acc.zero_()
+        self._run_segments(plan, plan.c_fwd, plan.fwd_segments, plan.stat_acc)
         if plan.training:
             self.flat.NBT[:len(plan.bns)] += 1
         self.last_plan = plan
@@ -154,10 +178,12 @@ class Engine:
         `model.named_parameters()` order, as views of the flat gradient buffer (None for frozen parameters)."""
         flat = self.flat
         flat.G.zero_()
-        plan.gstat.zero_()
+        if plan.comm is not None:
+            plan.comm.barrier()
+        plan.gstat_acc.zero_()
         plan.dWx.zero_()
         plan.y_out.dxd.copy_(dy.reshape(plan.y_out.dxd.shape))
-        self._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat, side=True)
+        self._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat_acc, side=True)
         # one copy of the 1.5 MB buffer: autograd may keep ("steal") the returned tensors as `.grad`, and the flat
         # buffer is zeroed again by the next backward (gradient accumulation over several backward calls must add up)
         out = flat.G.clone()
@@ -187,8 +213,18 @@ class Engine:
 
     # ---- data-parallel helpers -------------------------------------------------------------------
     def allreduce_grads(self, average: bool = True):
-        """One collective over the flat gradient buffer (replaces DDP's bucketed reducer, C1)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat.G)
-            if average:
-                self.flat.G.div_(dist.get_world_size())
+        """One collective over all parameter gradients (an alternative to wrapping the model in
+        DistributedDataParallel, whose bucket reducer also works: the gradients are autograd outputs)."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        grads = [p.grad for _, p in self._named if p.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        if average:
+            flat.div_(dist.get_world_size())
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()

@@ -601,7 +601,7 @@ class PlanBuilder:
 # =================================================================================================
 # materialisation: allocate buffers, build ctypes descriptors
 # =================================================================================================
-def allocate(plan: Plan, with_backward: bool, step_seed: Optional[torch.Tensor] = None):
+def allocate(plan: Plan, with_backward: bool, step_seed: Optional[torch.Tensor] = None, comm=None):
     dev = plan.device
     N = plan.N
     total = 0
@@ -638,6 +638,14 @@ def allocate(plan: Plan, with_backward: bool, step_seed: Optional[torch.Tensor] 
     nst = max(sum(2 * e.C for e in plan.bns), 2)
     plan.stat = torch.zeros(nst, dtype=torch.float64, device=dev)
     plan.gstat = torch.zeros(nst, dtype=torch.float64, device=dev)
+    # where the producers' epilogues accumulate: the same buffers on one GPU; with a peer-memory exchange (comm.py) this
+    # rank's partial sums live in symmetric memory and the BN_PREPARE kernels sum all ranks' parts into stat / gstat
+    plan.comm = comm
+    if comm is not None:
+        assert comm.n_stat >= nst, (comm.n_stat, nst)
+        plan.stat_acc, plan.gstat_acc = comm.stat_acc[:nst], comm.gstat_acc[:nst]
+    else:
+        plan.stat_acc, plan.gstat_acc = plan.stat, plan.gstat
     plan.Wx = torch.zeros(max(getattr(plan, "wx_numel", 0), 4), dtype=torch.float32, device=dev)
     plan.dWx = torch.zeros_like(plan.Wx)
     plan.coef = torch.zeros(4 * nst, dtype=torch.float32, device=dev)   # [C][8] per BN entry
@@ -661,6 +669,8 @@ def bn_table_struct(plan: Plan):
         s.running_var = flat.RB.data_ptr() + 4 * (e.rb_off + e.C)
         s.stat = plan.stat.data_ptr() + 8 * e.st_off
         s.gstat = plan.gstat.data_ptr() + 8 * e.st_off
+        s.stat_acc = plan.stat_acc.data_ptr() + 8 * e.st_off
+        s.gstat_acc = plan.gstat_acc.data_ptr() + 8 * e.st_off
         s.dgamma = flat.G.data_ptr() + 4 * e.gamma.off
         s.dbeta = flat.G.data_ptr() + 4 * e.beta.off
         s.coef = plan.coef.data_ptr() + 4 * (4 * e.st_off)
@@ -751,11 +761,16 @@ def to_c(plan: Plan, ops: List[Op]):
         c.n_bn = len(plan.bns)
         if op.kind in (_lib.BN_PREPARE_FWD, _lib.BN_PREPARE_BWD):
             c.n_bn, c.bn_lo = op.n_bn, op.bn_lo
+            if plan.comm is not None and op.sync_bn:
+                c.comm = plan.comm.dev_ptr          # statistic sum over NVLink peer memory fused into this kernel
     return arr
 
 
-def segments(ops: List[Op]) -> List[Tuple[int, int, List[int]]]:
-    """[(start, end, bn indices to all-reduce before running ops[start:end])]."""
+def segments(ops: List[Op], fused: bool = False) -> List[Tuple[int, int, List[int]]]:
+    """[(start, end, bn indices to all-reduce before running ops[start:end])].  `fused`: the statistic exchange is
+    inside the BN_PREPARE kernels (peer memory) - one segment, no host-issued collectives."""
+    if fused:
+        return [(0, len(ops), [])]
     segs, start, pend = [], 0, []
     for i, op in enumerate(ops):
         if op.sync_bn:
@@ -766,16 +781,16 @@ def segments(ops: List[Op]) -> List[Tuple[int, int, List[int]]]:
     return segs
 
 
-def finalize(plan: Plan, with_backward: bool, step_seed: Optional[torch.Tensor] = None):
+def finalize(plan: Plan, with_backward: bool, step_seed: Optional[torch.Tensor] = None, comm=None):
     """Allocate device memory and freeze the descriptors (device must be CUDA for execution)."""
-    allocate(plan, with_backward, step_seed)
+    allocate(plan, with_backward, step_seed, comm)
     tab = bn_table_struct(plan)
     raw = np.frombuffer(bytes(tab), dtype=np.uint8).copy()
     plan.bn_table_host = tab
     plan.bn_table_dev = torch.from_numpy(raw).to(plan.device)
     plan.c_fwd = to_c(plan, plan.fwd_ops)
-    plan.fwd_segments = segments(plan.fwd_ops)
+    plan.fwd_segments = segments(plan.fwd_ops, fused=comm is not None)
     if with_backward:
         plan.c_bwd = to_c(plan, plan.bwd_ops)
-        plan.bwd_segments = segments(plan.bwd_ops)
+        plan.bwd_segments = segments(plan.bwd_ops, fused=comm is not None)
     return plan

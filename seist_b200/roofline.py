@@ -110,6 +110,7 @@ def time_ops(plan: P.Plan, reps: int = 3, skip_kinds=(_lib.BN_FINALIZE_FWD,)) ->
                 e1.synchronize()
                 best.append(e0.elapsed_time(e1))
             ms = sorted(best)[len(best) // 2]
+            fam = lib.seist_op_family(base + i * size)
             rows.append(dict(phase=tag, index=i, name=op.name, kind=op.kind, ms=ms, bytes=op_bytes(op),
-                             flops=op_flops(op)))
+                             flops=op_flops(op), family=fam.decode() if fam else str(op.kind)))
     return rows

@@ -114,8 +114,11 @@ class Trainer:
         plan, eng, flat = self.plan, self.eng, self.flat
         s = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.seist_advance_seed(plan.step_seed.data_ptr(), s))
-        plan.stat.zero_()
-        eng._run_segments(plan, plan.c_fwd, plan.fwd_segments, plan.stat)
+        comm = plan.comm
+        if comm is not None:
+            comm.barrier()               # every peer has finished reading last step's partial statistics / gradients
+        plan.stat_acc.zero_()
+        eng._run_segments(plan, plan.c_fwd, plan.fwd_segments, plan.stat_acc)
         flat.NBT[:len(plan.bns)] += 1
         y, dy, t = plan.y_out.x, plan.y_out.dxd, self.t_static
         if isinstance(self.loss_fn, BCELoss):
@@ -131,15 +134,19 @@ class Trainer:
             _lib.check(lib.seist_huber_bwd(y.data_ptr(), t.data_ptr(), self.gout.data_ptr(), y.numel(),
                                            self.loss_fn.delta, dy.data_ptr(), s))
         flat.G.zero_()
-        plan.gstat.zero_()
+        plan.gstat_acc.zero_()
         plan.dWx.zero_()
-        eng._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat, side=True)
+        eng._run_segments(plan, plan.c_bwd, plan.bwd_segments, plan.gstat_acc, side=True)
         gscale = 1.0
+        grads = flat.G
         if self.world > 1:
-            dist.all_reduce(flat.G)            # one collective for all 1.5 MB of gradients (C1)
+            if comm is not None:
+                grads = comm.allreduce_grads()   # one kernel reading every peer's 1.5 MB over NVLink (C1), no NCCL
+            else:
+                dist.all_reduce(flat.G)          # NCCL fallback (SEIST_SYMM=0 / plain BatchNorm)
             gscale = 1.0 / self.world
         self.step_t += 1
-        _lib.check(lib.seist_adam_step(flat.P.data_ptr(), flat.G.data_ptr(), self.exp_avg.data_ptr(),
+        _lib.check(lib.seist_adam_step(flat.P.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(),
                                        self.exp_avg_sq.data_ptr(), flat.numel, self.lr_t.data_ptr(),
                                        self.step_t.data_ptr(), self.betas[0], self.betas[1], self.eps,
                                        self.weight_decay, 1 if self.decoupled else 0, gscale, s))
@@ -194,7 +201,9 @@ class Trainer:
         # world > 1: eager issue by default.  Capturing the NCCL all-reduces into the graph works and measured
         # 47.0 vs 47.9 ms/step on 2 GPUs, but the processes hung at teardown (graph holding NCCL work destroyed
         # after the process group) - experimental opt-in SEIST_DDP_GRAPH=1 until that is sorted out.
-        if self.use_graph and (self.world == 1 or os.environ.get("SEIST_DDP_GRAPH", "0") == "1"):
+        # world > 1: with the peer-memory exchange (comm.py) a step contains no NCCL call and is captured like on one
+        # GPU; the NCCL fallback is issued eagerly (capturing NCCL calls hung at teardown, opt-in SEIST_DDP_GRAPH=1)
+        if self.use_graph and (self.world == 1 or self.plan.comm is not None or os.environ.get("SEIST_DDP_GRAPH", "0") == "1"):
             if self.graph is None:
                 before = _lib.lib().seist_launch_count()
                 self._issue()                    # warm-up (also sets kernel attributes)

@@ -1,6 +1,9 @@
 import os
 import sys
 
+# kernels that wait for a peer kernel (csrc/comm.cu) must not have that peer blocked behind a lazy module load
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -63,3 +63,55 @@ def test_pad_and_sizes():
     assert R.upsampling_sizes(94, 6000, 6) == [187, 375, 750, 1501, 3001, 6000]
     assert R.head_layers(R.spec_for("seist_m_dpk")) == [(96, 64, 7), (64, 32, 7), (32, 24, 7), (24, 16, 7),
                                                          (16, 16, 7), (16, 6, 11)]
+
+
+@pytest.mark.skipif(not ri.available(), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("name", ["seist_s_dpk", "seist_m_dpk", "seist_l_dpk", "seist_m_emg"])
+def test_dropout_sites_and_rates_match_reference_modules(name):
+    """Every nn.Dropout / timm DropPath of the unmodified reference model (site = module path, rate = .p / .drop_prob,
+    models/seist.py:114,228,239,360-366,446,470,484; linspace schedule :705) must appear in the compiled plan as the
+    drop factor of the op that absorbs it, with the same probability — and the plan must not drop anywhere else."""
+    from seist_b200 import _lib
+    from seist_b200 import plan as P
+    from seist_b200.models import create_model
+    M = ri.import_reference_models()
+    ref = M.create_model(name, in_channels=3, in_samples=1024)
+    expect = {}
+    for path, mod in ref.named_modules():
+        cls = mod.__class__.__name__
+        if cls == "Dropout":
+            p = float(mod.p)
+        elif cls == "DropPath":
+            p = float(mod.drop_prob or 0.0)
+        else:
+            continue
+        head, leaf = path.rsplit(".", 1)
+        site = {
+            "droppath0": (head + ".proj", "p_path"),
+            "droppath1": (head + ".mlp.lin1", "p_path"),
+            "dropout": (head + ".lin1", "p_elem"),                 # MLP.dropout (head ends with .mlp)
+            "k_dropout": (head + ".k_proj", "p_elem"),
+            "attn_dropout": (head + ".core", "p_attn"),
+            "proj_dropout": (head + ".out_proj", "p_elem"),
+            "attn_droppath": (head + ".attention.out_proj", "p_path"),
+            "gconv_droppath": (head + ".gconv.mlp.lin1", "p_alpha"),
+            "mlp_droppath": (head + ".mlp.lin1", "p_path"),
+        }[leaf]
+        assert site not in expect, site
+        expect[site] = p
+    m = create_model(name, in_channels=3, in_samples=1024).train()
+    flat = P.FlatState(m, torch.device("cpu"))
+    plan = P.PlanBuilder(m, flat, 2, 1024, True).build()
+    got = {}
+    for op in plan.fwd_ops:
+        if op.kind not in (_lib.CONV_FWD, _lib.ATT_FWD):
+            continue
+        for field in ("p_elem", "p_path", "p_alpha", "p_attn"):
+            v = float(getattr(op, field))
+            if v > 0 or (op.name, field) in expect:
+                got[(op.name, field)] = v
+    missing = {k: v for k, v in expect.items() if abs(got.get(k, 0.0) - v) > 1e-7}
+    extra = {k: v for k, v in got.items() if v > 0 and k not in expect}
+    assert not missing, list(missing.items())[:8]
+    assert not extra, list(extra.items())[:8]
+    assert sum(1 for v in expect.values() if v > 0) >= 20

@@ -54,7 +54,9 @@ def test_fused_adam_matches_torch(wd, decoupled, gscale):
         torch.cuda.synchronize()
         upd_ref = (ref.detach() - p0).abs().max().item()
         err = (p - ref.detach()).abs().max().item()
-        assert err <= 2e-6 * max(upd_ref, 1e-3) + 1e-7, (i, err, upd_ref)
+        # the parameters are O(1): one fp32 ulp of a value in [2, 8) is 2.4e-7 .. 4.8e-7
+        assert err <= 1e-6, (i, err, upd_ref)
+        assert upd_ref > 0.5 * lr
     st = opt.state[ref]
     assert (m - st["exp_avg"]).abs().max().item() <= 1e-6 * st["exp_avg"].abs().max().item()
     assert (v - st["exp_avg_sq"]).abs().max().item() <= 1e-6 * st["exp_avg_sq"].abs().max().item()
@@ -105,6 +107,8 @@ def test_dropout_masks_follow_reference_semantics():
         _lib.check(_lib.lib().seist_plan_run(ctypes.addressof(pb.c_fwd), len(pb.fwd_ops), torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
     state = pb.arena.clone()
+    pa.coef.copy_(pb.coef)          # teacher forcing includes the BatchNorm coefficient tables of the consumer views
+    pa.stat.copy_(pb.stat)
     pa.step_seed.fill_(777)
     keeps = {"elem": [], "path": [], "alpha": []}
     checked = 0
@@ -302,7 +306,7 @@ def _train_parity(name, N, L, seed, out_tol=1e-3):
     x, tgt = R.synth_waveforms(N, L, seed=seed + 10)
     sd_g = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
             for k, v in sd.items()}
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(max(1, min(os.cpu_count() or 1, 32)))
     y_ref, _ = R.forward(sd_g, x, R.spec_for(name), training=True)
     loss_ref = R.bce_loss(y_ref, tgt)
     loss_ref.backward()
@@ -435,3 +439,106 @@ def test_trainer_state_dict_roundtrip_and_torch_layout():
         assert abs(sched(it) - ref.get_last_lr()[0]) <= 1e-12 + 1e-9 * ref.get_last_lr()[0], it
         dummy.step()
         ref.step()
+
+
+# ------------------------------------------------------------------------------------------------
+# the fused peer-memory exchange (csrc/comm.cu) with two virtual ranks in ONE process on ONE GPU: each rank's blob is an
+# ordinary device buffer and the "peer pointers" are the other rank's buffer; the two ranks run on two streams fed by two
+# host threads (the exchange kernels spin until the peer arrives), exactly the kernels a multi-GPU run executes
+# ------------------------------------------------------------------------------------------------
+def test_fused_peer_exchange_two_virtual_ranks_equal_single_rank():
+    from seist_b200.comm import PeerComm
+    name, L, NB, W = "seist_s_dpk", 2048, 8, 2
+    base = randomize(create_model(name, in_channels=3, in_samples=L), seed=5)
+    base.set_drop_rates(**ZERO_DROPS)
+    sd = {k: v.clone() for k, v in base.state_dict().items()}
+    x, t = R.synth_waveforms(NB, L, seed=3)
+    x, t = x.cuda(), t.cuda()
+    w = torch.tensor([0.5, 1.0, 1.0], device="cuda")
+    lib = _lib.lib()
+    dev = torch.device("cuda", 0)
+
+    def model_and_flat():
+        m = create_model(name, in_channels=3, in_samples=L)
+        m.load_state_dict(sd)
+        m.set_drop_rates(**ZERO_DROPS)
+        m = torch.nn.SyncBatchNorm.convert_sync_batchnorm(m).cuda().train()
+        return m, P.FlatState(m, dev)
+
+    # reference: one rank, whole batch
+    m1, f1 = model_and_flat()
+    p1 = P.finalize(P.PlanBuilder(m1, f1, NB, L, True, world=1).build(), True)
+    s0 = torch.cuda.current_stream().cuda_stream
+    p1.x_in.x.copy_(x)
+    p1.stat_acc.zero_()
+    _lib.check(lib.seist_plan_run(ctypes.addressof(p1.c_fwd), len(p1.fwd_ops), s0))
+    y = p1.y_out.x
+    gout = torch.ones(1, device="cuda")
+    _lib.check(lib.seist_bce_bwd(y.data_ptr(), t.data_ptr(), w.data_ptr(), gout.data_ptr(), NB, 3, L, 1e-6, p1.y_out.dxd.data_ptr(), s0))
+    f1.G.zero_(); p1.gstat_acc.zero_(); p1.dWx.zero_()
+    _lib.check(lib.seist_plan_run(ctypes.addressof(p1.c_bwd), len(p1.bwd_ops), s0))
+    torch.cuda.synchronize()
+
+    # two virtual ranks
+    ranks = [model_and_flat() for _ in range(W)]
+    n_stat = sum(2 * mod.num_features for mod in ranks[0][0].modules() if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm))
+    blobs, comms = [], []
+    # size of the blob: ask a throw-away layout computation
+    from seist_b200.comm import _align
+    nbytes = _align(8 * n_stat) * 2 + _align(4 * ranks[0][1].numel) + _align(4 * _lib.SIG_LANES * _lib.MAX_WORLD)
+    for r in range(W):
+        blobs.append(torch.zeros(nbytes, dtype=torch.uint8, device=dev))
+    bases = [b.data_ptr() for b in blobs]
+    for r in range(W):
+        comms.append(PeerComm(dev, W, r, n_stat, ranks[r][1].numel, blob=blobs[r], peer_bases=bases))
+        ranks[r][1].G = comms[r].grad
+    plans = [P.finalize(P.PlanBuilder(m, f, NB // W, L, True, world=W).build(), True, comm=comms[r])
+             for r, (m, f) in enumerate(ranks)]
+    assert any(op.kind == _lib.BN_PREPARE_FWD and op.sync_bn for op in plans[0].fwd_ops)
+    streams = [torch.cuda.Stream() for _ in range(W)]
+    n = NB // W
+    gos = [torch.ones(1, device="cuda") for _ in range(W)]
+    tts = [t[r * n:(r + 1) * n].contiguous() for r in range(W)]
+    torch.cuda.synchronize()
+
+    # one host thread feeds both ranks' streams, phase by phase (a phase is a few hundred asynchronous launches per rank;
+    # rank 0's stream waits inside its first exchange kernel until rank 1's stream gets there a few milliseconds later)
+    def phase(fn):
+        for r in range(W):
+            with torch.cuda.stream(streams[r]):
+                fn(r, plans[r], comms[r], ranks[r][1], streams[r].cuda_stream)
+        for st in streams:
+            st.synchronize()
+
+    def p_fwd(r, pl, cm, fl, s):
+        pl.x_in.x.copy_(x[r * n:(r + 1) * n])
+        cm.barrier(stream=s)
+        pl.stat_acc.zero_()
+        _lib.check(lib.seist_plan_run(ctypes.addressof(pl.c_fwd), len(pl.fwd_ops), s))
+
+    def p_bwd(r, pl, cm, fl, s):
+        yy = pl.y_out.x        # local-mean loss, like every rank of the real job (1/world is applied to the reduced sum)
+        _lib.check(lib.seist_bce_bwd(yy.data_ptr(), tts[r].data_ptr(), w.data_ptr(), gos[r].data_ptr(), n, 3, L, 1e-6,
+                                     pl.y_out.dxd.data_ptr(), s))
+        fl.G.zero_(); pl.gstat_acc.zero_(); pl.dWx.zero_()
+        _lib.check(lib.seist_plan_run(ctypes.addressof(pl.c_bwd), len(pl.bwd_ops), s))
+
+    def p_red(r, pl, cm, fl, s):
+        cm.allreduce_grads(stream=s)
+
+    phase(p_fwd)
+    phase(p_bwd)
+    phase(p_red)
+    torch.cuda.synchronize()
+    assert not any(c.timed_out() for c in comms), "a peer wait timed out"
+    y2 = torch.cat([p.y_out.x for p in plans])
+    assert (y2 - p1.y_out.x).abs().max().item() <= 2e-5 * p1.y_out.x.abs().max().item()
+    # every rank holds the same all-reduced gradient sum; / world = gradient of the global-mean loss
+    G1 = f1.G
+    for c in comms:
+        assert torch.equal(c.grad_red, comms[0].grad_red)           # fixed summation order: bit-identical on all ranks
+    G2 = comms[0].grad_red / W
+    assert (G2 - G1).abs().max().item() <= 3e-4 * G1.abs().max().item(), (G2 - G1).abs().max().item()
+    for p in plans:
+        assert (p.flat.RB - p1.flat.RB).abs().max().item() <= 1e-5 * (p1.flat.RB.abs().max().item() + 1e-3)
+        assert torch.equal(p.stat, plans[0].stat) and torch.equal(p.gstat, plans[0].gstat)
