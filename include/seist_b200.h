@@ -233,6 +233,24 @@ int seist_comm_allreduce(const SeistComm* comm, int32_t world, float* out, int64
 int seist_comm_barrier(const SeistComm* comm, int32_t lane, void* stream);
 uint64_t seist_sizeof_comm(void);
 
+/* ---- post-processing on the device (reference training/postprocess.py, utils/metrics.py) -----------
+   prob: (N, C, L) fp32 probabilities (the dpk head's output); `channel` selects the trace.
+   seist_pick_phase   = _pick_phase (postprocess.py:161-193 -> _detect_peaks :15-111, rising edges, mph = threshold,
+                        mpd = min_peak_dist > 1, topk): out (N, topk) int64 sample indices, padded with pad_value.
+   seist_detect_event = _detect_event (:114-158 -> obspy trigger_onset(x, thr, thr)): out (N, 2*topk) int64 [on, off]
+                        pairs of the topk longest runs of prob > thr, padded with [1, 0].
+   seist_pick_counters / seist_det_counters = the tp / predp / possp (+ residual sums) of utils/metrics.py:141-232,
+                        ADDED into a double vector `acc` (pick: 7 entries, det: 4) so that several tasks and steps share
+                        one buffer and one all-reduce.  Integer results are bit-identical to oracle/postprocess_ref.py. */
+int seist_pick_phase(const float* prob, int64_t N, int32_t C, int32_t channel, int32_t L, float threshold,
+                     int32_t min_peak_dist, int32_t topk, int64_t pad_value, int64_t* out, void* stream);
+int seist_detect_event(const float* prob, int64_t N, int32_t C, int32_t channel, int32_t L, float threshold,
+                       int32_t topk, int64_t* out, void* stream);
+int seist_pick_counters(const int64_t* targets, const int64_t* preds, int64_t n, int32_t num_samples, int32_t t_thres,
+                        double* acc, void* stream);
+int seist_det_counters(const int64_t* targets, const int64_t* preds, int64_t N, int32_t k_targets, int32_t k_preds,
+                       int32_t num_samples, double* acc, void* stream);
+
 /* *seed += 1 (device scalar), keeps dropout streams distinct across graph replays */
 int seist_advance_seed(uint64_t* seed, void* stream);
 

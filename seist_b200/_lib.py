@@ -116,6 +116,17 @@ def lib():
                                   C.c_float, C.c_void_p]
     L.seist_advance_seed.restype = C.c_int
     L.seist_advance_seed.argtypes = [C.c_void_p, C.c_void_p]
+    L.seist_pick_phase.restype = C.c_int
+    L.seist_pick_phase.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32,
+                                   C.c_int64, C.c_void_p, C.c_void_p]
+    L.seist_detect_event.restype = C.c_int
+    L.seist_detect_event.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,
+                                     C.c_void_p, C.c_void_p]
+    L.seist_pick_counters.restype = C.c_int
+    L.seist_pick_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.seist_det_counters.restype = C.c_int
+    L.seist_det_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p]
     L.seist_sizeof_comm.restype = C.c_uint64
     L.seist_comm_barrier.restype = C.c_int
     L.seist_comm_barrier.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -137,6 +148,7 @@ EXPORTS = [
     "seist_abi_version", "seist_sizeof_op", "seist_sizeof_bn", "seist_last_error", "seist_launch_count",
     "seist_tc_error_flag", "seist_plan_run", "seist_plan_run2", "seist_bce_fwd", "seist_bce_bwd", "seist_huber_fwd", "seist_huber_bwd",
     "seist_adam_step", "seist_advance_seed", "seist_comm_allreduce", "seist_comm_barrier", "seist_sizeof_comm", "seist_op_family",
+    "seist_pick_phase", "seist_detect_event", "seist_pick_counters", "seist_det_counters",
 ]
 
 
