@@ -251,6 +251,16 @@ int seist_pick_counters(const int64_t* targets, const int64_t* preds, int64_t n,
 int seist_det_counters(const int64_t* targets, const int64_t* preds, int64_t N, int32_t k_targets, int32_t k_preds,
                        int32_t num_samples, double* acc, void* stream);
 
+/* ---- input side on the device (reference training/preprocess.py) ---------------------------------------
+   seist_normalize  = DataPreprocessor._normalize (:224-242) over `rows` traces of L samples, in place: mean removal,
+                      then mode 1 "std" / 2 "max" scaling (a zero scale is replaced by 1), mode 0 "" mean removal only.
+   seist_dpk_labels = the label stack [det, ppk, spk] of the dpk task (config.py:137-146) from the phase indices:
+                      _generate_soft_label (:544-683) with _pad_phases (:16-35).  ppks / spks: (N, K) int64, entries
+                      <= -1000000 mean "no phase"; shape 0 gaussian (sigma 10 samples) / 1 triangle / 2 box; out (N,3,L). */
+int seist_normalize(float* x, int64_t rows, int32_t L, int32_t mode, void* stream);
+int seist_dpk_labels(const int64_t* ppks, const int64_t* spks, int64_t N, int32_t K, int32_t L, int32_t width,
+                     int32_t shape, float coda_ratio, float* out, void* stream);
+
 /* *seed += 1 (device scalar), keeps dropout streams distinct across graph replays */
 int seist_advance_seed(uint64_t* seed, void* stream);
 

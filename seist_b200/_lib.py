@@ -127,6 +127,11 @@ def lib():
     L.seist_det_counters.restype = C.c_int
     L.seist_det_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_void_p]
+    L.seist_normalize.restype = C.c_int
+    L.seist_normalize.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    L.seist_dpk_labels.restype = C.c_int
+    L.seist_dpk_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_float, C.c_void_p, C.c_void_p]
     L.seist_sizeof_comm.restype = C.c_uint64
     L.seist_comm_barrier.restype = C.c_int
     L.seist_comm_barrier.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -149,6 +154,7 @@ EXPORTS = [
     "seist_tc_error_flag", "seist_plan_run", "seist_plan_run2", "seist_bce_fwd", "seist_bce_bwd", "seist_huber_fwd", "seist_huber_bwd",
     "seist_adam_step", "seist_advance_seed", "seist_comm_allreduce", "seist_comm_barrier", "seist_sizeof_comm", "seist_op_family",
     "seist_pick_phase", "seist_detect_event", "seist_pick_counters", "seist_det_counters",
+    "seist_normalize", "seist_dpk_labels",
 ]
 
 

@@ -8,7 +8,7 @@
 
 namespace seist {
 
-static char g_err[512] = "";
+static thread_local char g_err[512] = "";      // last error text of the calling thread
 static std::atomic<uint64_t> g_launches{0};
 static int g_sm_count = 0;
 
@@ -245,14 +245,26 @@ uint64_t seist_launch_count(void) { return seist::g_launches.load(); }
 const char* seist_op_family(const SeistOp* op) { return op ? seist::kFamilyName[seist::choose(*op)] : "none"; }
 int seist_tc_error_flag(void) { return seist::pw_tc_error_flag() | seist::bww_tc_error_flag() | seist::tcconv_error_flag(); }
 
-static std::vector<cudaEvent_t> g_events;
+// fork/join events of seist_plan_run2, one pool per device (events belong to the device that was current at creation)
+static std::vector<cudaEvent_t> g_events[64];
 static cudaEvent_t event_at(size_t i) {
-  while (g_events.size() <= i) {
-    cudaEvent_t e;
-    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    g_events.push_back(e);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::vector<cudaEvent_t>& pool = g_events[dev & 63];
+  while (pool.size() <= i) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    pool.push_back(e);
   }
-  return g_events[i];
+  return pool[i];
+}
+static int fork_join(cudaStream_t from, cudaStream_t to, size_t& ev) {
+  cudaEvent_t e = event_at(ev++);
+  if (e == nullptr) { seist::set_error("plan_run2: cudaEventCreate failed"); return (int)cudaErrorMemoryAllocation; }
+  cudaError_t r = cudaEventRecord(e, from);
+  if (r == cudaSuccess) r = cudaStreamWaitEvent(to, e, 0);
+  if (r != cudaSuccess) { seist::set_error(cudaGetErrorString(r)); return (int)r; }
+  return 0;
 }
 
 int seist_plan_run2(const SeistOp* ops, int32_t n, void* stream, void* side_stream) {
@@ -266,9 +278,8 @@ int seist_plan_run2(const SeistOp* ops, int32_t n, void* stream, void* side_stre
     int rc;
     if (on_side) {
       if (main_dirty) {      // order after everything issued on the main stream so far
-        cudaEvent_t e = event_at(ev++);
-        cudaEventRecord(e, s);
-        cudaStreamWaitEvent(side, e, 0);
+        const int fr = fork_join(s, side, ev);
+        if (fr) return fr;
         main_dirty = false;
       }
       rc = seist::run_one(ops[i], side);
@@ -281,15 +292,11 @@ int seist_plan_run2(const SeistOp* ops, int32_t n, void* stream, void* side_stre
       char buf[600];
       std::snprintf(buf, sizeof(buf), "op %d (kind %d): %s", i, ops[i].kind, seist::g_err);
       seist::set_error(buf);
-      if (forked) { cudaEvent_t e = event_at(ev++); cudaEventRecord(e, side); cudaStreamWaitEvent(s, e, 0); }
+      if (forked) fork_join(side, s, ev);
       return rc;
     }
   }
-  if (forked) {
-    cudaEvent_t e = event_at(ev++);
-    cudaEventRecord(e, side);
-    cudaStreamWaitEvent(s, e, 0);
-  }
+  if (forked) return fork_join(side, s, ev);
   return 0;
 }
 

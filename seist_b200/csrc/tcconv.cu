@@ -807,11 +807,13 @@ static bool tcc_geometry(const SeistOp& op, int mode, TccGeom& g) {
 
 template <int MODE, bool G, bool E>
 static int tcc_go(const SeistOp& op, const TccGeom& g, const TccMaps& maps, unsigned grid, cudaStream_t s) {
-  static size_t max_set = 0;
-  if ((size_t)g.smem_bytes > max_set) {
+  static bool attr_set[64] = {false};        // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(tcconv_kernel<MODE, G, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
-    max_set = 227 * 1024;
+    attr_set[dev & 63] = true;
   }
   tcconv_kernel<MODE, G, E><<<grid, TCC_NT, g.smem_bytes, s>>>(op, g, maps);
   return 0;

@@ -145,6 +145,7 @@ class Trainer:
             else:
                 dist.all_reduce(flat.G)          # NCCL fallback (SEIST_SYMM=0 / plain BatchNorm)
             gscale = 1.0 / self.world
+        self.last_grads = grads            # what the optimizer consumed: the rank-summed gradients (x gscale = mean)
         self.step_t += 1
         _lib.check(lib.seist_adam_step(flat.P.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(),
                                        self.exp_avg_sq.data_ptr(), flat.numel, self.lr_t.data_ptr(),
