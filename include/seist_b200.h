@@ -57,7 +57,8 @@ typedef struct SeistBN {
   float eps;
   float momentum;
   float grad_scale;      /* multiplies dgamma/dbeta (1/world_size under data parallelism)         */
-  int32_t pad_;
+  int32_t inline_coef;   /* 1: consumers derive the coefficients from stat / gstat themselves while resolving their views
+                            (no BN_PREPARE launches: single-GPU training); 0: read the `coef` table           */
 } SeistBN;
 
 /* ---- data-parallel exchange over NVLink peer memory (replaces the per-BatchNorm NCCL calls of
@@ -213,6 +214,12 @@ int seist_bce_fwd(const float* preds, const float* targets, const float* weight,
 /* dpreds = gout * dloss/dpreds  (gout: device scalar, upstream gradient of the mean loss) */
 int seist_bce_bwd(const float* preds, const float* targets, const float* weight, const float* gout,
                   int64_t N, int32_t C, int64_t L, float eps, float* dpreds, void* stream);
+/* CELoss(weight) on class probabilities (N, C): mean_n sum_c -w[c] t[n,c] log(p[n,c] + eps) - models/loss.py:8-29,
+   the loss of the seist_*_pmp variants (config.py:147-155) */
+int seist_ce_fwd(const float* preds, const float* targets, const float* weight, int64_t rows, int32_t C, float eps,
+                 double* loss_sum, float* loss_out, void* stream);
+int seist_ce_bwd(const float* preds, const float* targets, const float* weight, const float* gout, int64_t rows,
+                 int32_t C, float eps, float* dpreds, void* stream);
 /* torch.nn.HuberLoss(delta) mean — models/loss.py:3, config.py:158 */
 int seist_huber_fwd(const float* preds, const float* targets, int64_t numel, float delta,
                     double* loss_sum, float* loss_out, void* stream);
@@ -259,7 +266,7 @@ int seist_det_counters(const int64_t* targets, const int64_t* preds, int64_t N, 
                       <= -1000000 mean "no phase"; shape 0 gaussian (sigma 10 samples) / 1 triangle / 2 box; out (N,3,L). */
 int seist_normalize(float* x, int64_t rows, int32_t L, int32_t mode, void* stream);
 int seist_dpk_labels(const int64_t* ppks, const int64_t* spks, int64_t N, int32_t K, int32_t L, int32_t width,
-                     int32_t shape, float coda_ratio, float* out, void* stream);
+                     int32_t shape, double coda_ratio, float* out, void* stream);
 
 /* *seed += 1 (device scalar), keeps dropout streams distinct across graph replays */
 int seist_advance_seed(uint64_t* seed, void* stream);

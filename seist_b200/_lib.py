@@ -22,7 +22,7 @@ class SeistBN(C.Structure):
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("coef", C.c_void_p),
         ("count", C.c_double),
         ("C", C.c_int32), ("chain", C.c_int32), ("use_batch", C.c_int32), ("is_chained", C.c_int32),
-        ("eps", C.c_float), ("momentum", C.c_float), ("grad_scale", C.c_float), ("pad_", C.c_int32),
+        ("eps", C.c_float), ("momentum", C.c_float), ("grad_scale", C.c_float), ("inline_coef", C.c_int32),
     ]
 
 
@@ -104,6 +104,12 @@ def lib():
     L.seist_bce_bwd.restype = C.c_int
     L.seist_bce_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                 C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
+    L.seist_ce_fwd.restype = C.c_int
+    L.seist_ce_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                               C.c_void_p]
+    L.seist_ce_bwd.restype = C.c_int
+    L.seist_ce_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
+                               C.c_void_p]
     L.seist_huber_fwd.restype = C.c_int
     L.seist_huber_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
                                   C.c_void_p]
@@ -131,7 +137,7 @@ def lib():
     L.seist_normalize.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     L.seist_dpk_labels.restype = C.c_int
     L.seist_dpk_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                   C.c_float, C.c_void_p, C.c_void_p]
+                                   C.c_double, C.c_void_p, C.c_void_p]
     L.seist_sizeof_comm.restype = C.c_uint64
     L.seist_comm_barrier.restype = C.c_int
     L.seist_comm_barrier.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -154,7 +160,7 @@ EXPORTS = [
     "seist_tc_error_flag", "seist_plan_run", "seist_plan_run2", "seist_bce_fwd", "seist_bce_bwd", "seist_huber_fwd", "seist_huber_bwd",
     "seist_adam_step", "seist_advance_seed", "seist_comm_allreduce", "seist_comm_barrier", "seist_sizeof_comm", "seist_op_family",
     "seist_pick_phase", "seist_detect_event", "seist_pick_counters", "seist_det_counters",
-    "seist_normalize", "seist_dpk_labels",
+    "seist_normalize", "seist_dpk_labels", "seist_ce_fwd", "seist_ce_bwd",
 ]
 
 

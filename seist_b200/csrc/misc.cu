@@ -321,6 +321,24 @@ __global__ void __launch_bounds__(256) huber_bwd_kernel(const float* __restrict_
   }
 }
 
+// CELoss (reference models/loss.py:8-29): mean over rows of sum_c -w[c] * t[c] * log(p[c] + eps); preds are probabilities
+// (the classification head ends in a softmax, models/seist.py:575-591)
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ p, const float* __restrict__ t,
+                                                     const float* __restrict__ w, int64_t total, int C, float eps, double* acc) {
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    s -= w[i % C] * t[i] * logf(p[i] + eps);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(acc, (double)s);
+}
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t,
+                                                     const float* __restrict__ w, const float* __restrict__ gout, int64_t total,
+                                                     int C, float eps, float inv_rows, float* __restrict__ d) {
+  const float g = *gout * inv_rows;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = -g * w[i % C] * t[i] / (p[i] + eps);
+}
+
 static int ew_grid(int64_t total) {
   int64_t g = (total + 256 * 8 - 1) / (256 * 8);
   if (g < 1) g = 1;
@@ -387,6 +405,27 @@ int seist_bce_bwd(const float* preds, const float* targets, const float* weight,
                                                 (float)(1.0 / (double)total), dpreds);
   note_launch();
   return check_launch("bce_bwd");
+}
+
+int seist_ce_fwd(const float* preds, const float* targets, const float* weight, int64_t rows, int32_t C, float eps,
+                 double* loss_sum, float* loss_out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rows <= 0 || C <= 0) return -1;
+  cudaMemsetAsync(loss_sum, 0, sizeof(double), s);
+  ce_fwd_kernel<<<ew_grid(rows * C), 256, 0, s>>>(preds, targets, weight, rows * C, C, eps, loss_sum);
+  note_launch();
+  mean_finalize_kernel<<<1, 1, 0, s>>>(loss_sum, 1.0 / (double)rows, loss_out);
+  note_launch();
+  return check_launch("ce_fwd");
+}
+
+int seist_ce_bwd(const float* preds, const float* targets, const float* weight, const float* gout, int64_t rows, int32_t C,
+                 float eps, float* dpreds, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rows <= 0 || C <= 0) return -1;
+  ce_bwd_kernel<<<ew_grid(rows * C), 256, 0, s>>>(preds, targets, weight, gout, rows * C, C, eps, (float)(1.0 / (double)rows), dpreds);
+  note_launch();
+  return check_launch("ce_bwd");
 }
 
 int seist_huber_fwd(const float* preds, const float* targets, int64_t numel, float delta, double* loss_sum,

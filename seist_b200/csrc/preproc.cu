@@ -71,7 +71,7 @@ __device__ __forceinline__ double pr_soft(const long long* idx, int n, int j, in
 
 // out (N, 3, L): det, ppk, spk
 __global__ void __launch_bounds__(PR_NT) dpk_labels_kernel(const long long* __restrict__ ppks, const long long* __restrict__ spks, int K,
-                                                           int L, int width, int shape, float coda_ratio, float* __restrict__ out) {
+                                                           int L, int width, int shape, double coda_ratio, float* __restrict__ out) {
   __shared__ long long p_s[PR_MAXK], s_s[PR_MAXK], pp_s[2 * PR_MAXK], ss_s[2 * PR_MAXK];
   __shared__ int np_s, ns_s, npair_s;
   const int n = blockIdx.x;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(PR_NT) dpk_labels_kernel(const long long* __re
     double det = 0.0;
     for (int a = 0; a < npair_s; ++a) {
       const long long ppk = pp_s[a], spk = ss_s[a];
-      const long long dte = (long long)((double)spk + (double)coda_ratio * (double)(spk - ppk));   // int(): truncation
+      const long long dte = (long long)((double)spk + coda_ratio * (double)(spk - ppk));   // python int(): truncation, in double
       const long long two[2] = {ppk, dte};
       double li = pr_soft(two, 2, j, L, left, right, width, shape);
       const long long c0 = ppk < 0 ? 0 : (ppk > L ? L : ppk), c1 = dte < 0 ? 0 : (dte > L ? L : dte);
@@ -134,7 +134,7 @@ int seist_normalize(float* x, int64_t rows, int32_t L, int32_t mode, void* strea
 }
 
 int seist_dpk_labels(const int64_t* ppks, const int64_t* spks, int64_t N, int32_t K, int32_t L, int32_t width, int32_t shape,
-                     float coda_ratio, float* out, void* stream) {
+                     double coda_ratio, float* out, void* stream) {
   if (!ppks || !spks || !out || N <= 0 || K < 1 || K > PR_MAXK || L <= 0 || width < 1 || shape < 0 || shape > 2) {
     set_error("dpk_labels: bad arguments (1 <= K <= 8, shape 0 gaussian / 1 triangle / 2 box)");
     return -1;

@@ -109,10 +109,24 @@ class Engine:
         from .comm import PeerComm, symmetric_memory_enabled
         if world <= 1 or not symmetric_memory_enabled():
             return None
-        if self.comm is None:
+        if self.comm is None and not getattr(self, "_comm_failed", False):
             n_stat = sum(2 * m.num_features for m in self.model.modules()
                          if isinstance(m, nn.modules.batchnorm._BatchNorm))
-            self.comm = PeerComm(self.flat.device, world, dist.get_rank(), max(n_stat, 2), self.flat.numel)
+            ok = torch.ones(1, device=self.flat.device)
+            try:
+                if world > _lib.MAX_WORLD:
+                    raise RuntimeError(f"more than {_lib.MAX_WORLD} ranks")
+                comm = PeerComm(self.flat.device, world, dist.get_rank(), max(n_stat, 2), self.flat.numel)
+            except Exception as e:      # noqa: BLE001 - e.g. no peer access / symmetric memory unsupported on this box
+                comm = None
+                ok.zero_()
+                import warnings
+                warnings.warn(f"seist_b200: NVLink peer-memory exchange unavailable ({e!r}); using NCCL collectives")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # all ranks take the same path
+            if ok.item() < 1:
+                self._comm_failed = True
+                return None
+            self.comm = comm
             self.flat.G = self.comm.grad
             self.flat.G.zero_()
         return self.comm

@@ -122,8 +122,33 @@ class HuberLoss(nn.Module):
         return _HuberFn.apply(preds.float(), targets.to(device=preds.device, dtype=torch.float32), self.delta)
 
 
-# ---- losses of tasks outside the accelerated path (kept for the registry surface) ---------------
+class _CEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, preds, targets, wvec, eps):
+        n, c = preds.shape
+        acc = torch.empty(1, dtype=torch.float64, device=preds.device)
+        out = torch.empty((), dtype=torch.float32, device=preds.device)
+        _lib.check(_lib.lib().seist_ce_fwd(preds.data_ptr(), targets.data_ptr(), wvec.data_ptr(), n, c, eps, acc.data_ptr(),
+                                           out.data_ptr(), _stream()), "seist_ce_fwd")
+        ctx.save_for_backward(preds, targets, wvec)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        preds, targets, wvec = ctx.saved_tensors
+        n, c = preds.shape
+        d = torch.empty_like(preds)
+        gout = gout.contiguous().float()
+        _lib.check(_lib.lib().seist_ce_bwd(preds.data_ptr(), targets.data_ptr(), wvec.data_ptr(), gout.data_ptr(), n, c, ctx.eps,
+                                           d.data_ptr(), _stream()), "seist_ce_bwd")
+        return d, None, None, None
+
+
 class CELoss(nn.Module):
+    """mean_n sum_c -w[c] * t[n, c] * log(p[n, c] + eps) on class probabilities (reference models/loss.py:8-29; the loss of
+    the seist_*_pmp variants, config.py:147-155).  Fused CUDA kernels for (N, C) CUDA tensors; other shapes (other
+    models' uses) fall back to the reference's torch expression."""
     _epsilon = 1e-6
 
     def __init__(self, weight=None) -> None:
@@ -131,7 +156,16 @@ class CELoss(nn.Module):
         self.register_buffer("weight", _as_weight(weight, self._get_name()))
 
     def forward(self, preds, targets):
+        if preds.is_cuda and preds.dim() == 2 and targets.shape == preds.shape and self.weight.numel() in (1, preds.shape[1]):
+            c = preds.shape[1]
+            w = self.weight.to(preds.device, torch.float32)
+            wvec = (w.reshape(1).expand(c) if w.numel() == 1 else w.reshape(c)).contiguous()
+            return _CEFn.apply(preds.contiguous().float(), targets.to(device=preds.device, dtype=torch.float32).contiguous(),
+                               wvec, float(self._epsilon))
         return (-(targets * (preds + self._epsilon).log()) * self.weight).sum(1).mean()
+
+
+# ---- losses of tasks outside the accelerated path (kept for the registry surface) ---------------
 
 
 class MSELoss(nn.Module):

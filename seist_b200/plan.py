@@ -223,6 +223,11 @@ class PlanBuilder:
         self.plan = Plan()
         self.mods = dict(model.named_modules())
         self.seed_ctr = 1
+        # SEIST_BN_INLINE=1 (single-GPU training): no BN_PREPARE launches (216 per seist_m_dpk step), every consumer CTA
+        # derives the per-channel coefficients from the statistics while it resolves its views.  Measured on B200: 596
+        # instead of 812 launches but 43.2 instead of 41.1 ms/step - the fp64 divisions / rsqrt repeated by every CTA cost
+        # more than the launches they save (gpurun_out/bench_r2h.json) - so the separate launches stay the default.
+        self.inline_coef = bool(training and world == 1 and os.environ.get("SEIST_BN_INLINE", "0") == "1")
         self._bn_idx: Dict[str, int] = {}
         self._st_off = 0
         self._wx_off = 0
@@ -467,6 +472,7 @@ class PlanBuilder:
     def build(self) -> Plan:
         hp, pl = self.hp, self.plan
         pl.N, pl.L, pl.training, pl.world, pl.device, pl.flat = self.N, self.Lx, self.training, self.world, self.device, self.flat
+        pl.inline_coef = self.inline_coef
         xin = self.buf("x", hp.in_channels, self.Lx, no_grad=True)
         pl.x_in = xin
         cur = View(xin, 0, hp.in_channels)
@@ -573,6 +579,8 @@ class PlanBuilder:
         nb = len(self.plan.bns)
         if forward and not self.training:
             return [Op(kind, self.N, bn_lo=0, n_bn=nb, name="bn_prepare_all")] + ops
+        if self.inline_coef:
+            return ops          # single-GPU training: the consumers derive the coefficients themselves (SeistBN.inline_coef)
         out: List[Op] = []
         ready = set()
         for op in ops:
@@ -682,6 +690,7 @@ def bn_table_struct(plan: Plan):
         s.eps = 1e-5
         s.momentum = 0.1
         s.grad_scale = 1.0 / plan.world
+        s.inline_coef = 1 if getattr(plan, "inline_coef", False) else 0
     return arr
 
 

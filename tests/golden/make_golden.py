@@ -21,7 +21,10 @@ FIXTURES = [  # (model, checkpoint, batch, length)
     ("seist_s_dpk", "seist_s_dpk_diting.pth", 4, 8192),   # BASELINE.json configs[0]
     ("seist_m_dpk", "seist_m_dpk_diting.pth", 2, 8192),
     ("seist_m_emg", "seist_m_emg_diting.pth", 2, 8192),
+    ("seist_s_pmp", "seist_s_pmp_diting.pth", 4, 8192),    # HeadClassification + CELoss(weight=[1, 1]) (config.py:147-155)
+    ("seist_s_baz", "seist_s_baz_diting.pth", 4, 8192),    # HeadRegression x 360 + HuberLoss (config.py:167-175)
 ]
+ONLY = set(sys.argv[1:])      # python make_golden.py seist_s_pmp seist_s_baz  -> only these (the others stay byte-identical)
 
 
 def main():
@@ -29,13 +32,20 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     for name, ck, n, length in FIXTURES:
+        if ONLY and name not in ONLY:
+            continue
         blob = torch.load(os.path.join(ri.REF_ROOT, "pretrained", ck), map_location="cpu")
         sd = blob["model_dict"] if "model_dict" in blob else blob
         model = M.create_model(name, in_channels=3, in_samples=length)
         model.load_state_dict(sd, strict=True)
         ri.zero_drop_rates(model)
         x, tgt = R.synth_waveforms(n, length, seed=20240921)
-        if not name.endswith("dpk"):
+        if name.endswith("pmp"):
+            cls = torch.randint(0, 2, (n,), generator=torch.Generator().manual_seed(5))
+            tgt = torch.nn.functional.one_hot(cls, 2).float()
+        elif name.endswith("baz"):
+            tgt = torch.rand(n, 1, generator=torch.Generator().manual_seed(5)) * 360.0
+        elif not name.endswith("dpk"):
             tgt = torch.rand(n, 1, generator=torch.Generator().manual_seed(5)) * 8.0
         model.eval()
         with torch.no_grad():
@@ -44,6 +54,8 @@ def main():
         y_train = model(x)
         if name.endswith("dpk"):
             loss = M.BCELoss(weight=[[0.5], [1], [1]])(y_train, tgt)
+        elif name.endswith("pmp"):
+            loss = M.CELoss(weight=[1, 1])(y_train, tgt)
         else:
             loss = M.HuberLoss()(y_train, tgt)
         loss.backward()

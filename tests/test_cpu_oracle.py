@@ -11,7 +11,7 @@ from oracle import seist_ref as R
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["seist_s_dpk", "seist_m_dpk", "seist_m_emg"])
+@pytest.mark.parametrize("name", ["seist_s_dpk", "seist_m_dpk", "seist_m_emg", "seist_s_pmp", "seist_s_baz"])
 def test_oracle_matches_golden(name):
     g = torch.load(os.path.join(GOLD, f"{name}.pt"))
     spec = R.spec_for(name)

@@ -56,7 +56,7 @@ def _check_grads(model, ref_grads, rtol=2e-3, floor=1e-5):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["seist_s_dpk", "seist_m_dpk", "seist_m_emg"])
+@pytest.mark.parametrize("name", ["seist_s_dpk", "seist_m_dpk", "seist_m_emg", "seist_s_pmp", "seist_s_baz"])
 def test_eval_matches_reference_golden(name):
     g, m = _load(name)
     m.eval()
@@ -71,7 +71,7 @@ def test_eval_matches_reference_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["seist_s_dpk", "seist_m_dpk", "seist_m_emg"])
+@pytest.mark.parametrize("name", ["seist_s_dpk", "seist_m_dpk", "seist_m_emg", "seist_s_pmp", "seist_s_baz"])
 def test_train_step_matches_reference_golden(name):
     g, m = _load(name)
     m.set_drop_rates(**ZERO)
@@ -81,6 +81,9 @@ def test_train_step_matches_reference_golden(name):
     assert (y.detach().cpu() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
     if name.endswith("dpk"):
         loss = BCELoss(weight=[[0.5], [1], [1]])(y, g["target"].cuda())
+    elif name.endswith("pmp"):
+        from seist_b200.models.loss import CELoss
+        loss = CELoss(weight=[1, 1])(y, g["target"].cuda())          # fused CUDA CE (config.py:147-155)
     else:
         loss = HuberLoss()(y, g["target"].cuda())
     assert abs(loss.item() - g["loss"].item()) <= 1e-4 * abs(g["loss"].item())
