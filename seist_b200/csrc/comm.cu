@@ -22,12 +22,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
   double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ float4 ld_relaxed_sys_f32x4(const float* p) {
   float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 
@@ -69,9 +69,15 @@ __global__ void __launch_bounds__(256) bn_prepare_xchg_kernel(const SeistBN* tab
     double* red = fwd ? e.stat : e.gstat;
     const ptrdiff_t off = acc - (fwd ? comm->stat_peer[comm->rank] : comm->gstat_peer[comm->rank]);
     for (int i = threadIdx.x; i < 2 * e.C; i += blockDim.x) {
+      // all peer loads in flight at once (one NVLink round trip, not world - 1), then a fixed-order sum: bit-identical on
+      // every rank
+      double v[SEIST_MAX_WORLD];
+#pragma unroll
+      for (int p = 0; p < SEIST_MAX_WORLD; ++p)
+        v[p] = p < world ? ld_relaxed_sys_f64((fwd ? comm->stat_peer[p] : comm->gstat_peer[p]) + off + i) : 0.0;
       double s = 0.0;
-      for (int p = 0; p < world; ++p)                      // fixed order: bit-identical sums on every rank
-        s += ld_relaxed_sys_f64((fwd ? comm->stat_peer[p] : comm->gstat_peer[p]) + off + i);
+#pragma unroll
+      for (int p = 0; p < SEIST_MAX_WORLD; ++p) s += v[p];
       red[i] = s;
     }
   }
@@ -104,10 +110,14 @@ __global__ void __launch_bounds__(256) comm_allreduce_kernel(const SeistComm* co
   const int world = comm->world;
   const int64_t nq = numel >> 2;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    float4 v[SEIST_MAX_WORLD];                             // every peer's load in flight before the first use
+#pragma unroll
+    for (int p = 0; p < SEIST_MAX_WORLD; ++p)
+      v[p] = p < world ? ld_relaxed_sys_f32x4(comm->grad_peer[p] + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < world; ++p) {                      // fixed order: every rank computes the same bits
-      const float4 v = ld_relaxed_sys_f32x4(comm->grad_peer[p] + 4 * q);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+#pragma unroll
+    for (int p = 0; p < SEIST_MAX_WORLD; ++p) {            // fixed order: every rank computes the same bits
+      s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w;
     }
     *reinterpret_cast<float4*>(out + 4 * q) = s;
   }
