@@ -103,6 +103,7 @@ static int tcc_mode() {
 }
 static bool tcc_auto(const SeistOp& op, int mode) {
   const int Kd = mode == 0 ? op.Cin : op.Cout, Nd = mode == 0 ? op.Cout : op.Cin;
+  if (op.up_src_L > 0) return mode == 0 && Kd >= 16;     // dpk head: 33 % of the FLOPs, k = 7 / 11 dense taps
   if (op.k > 1) return op.L_out <= 512 && Kd >= 8 && Nd >= 8;
   if (mode == 0) return Kd >= 64 && Nd >= 48;
   return Kd >= 96 && Nd >= 96;

@@ -51,6 +51,8 @@ struct TccGeom {
   int b_part;           // bytes of one precision part of one chunk's weights: k * (KC/4) * N_pad * 16
   int a_stage;          // bytes of one panel stage: 2 * a_part (+ 2 * b_part when the weights are streamed)
   int has_dxd, has_bn, need_x;
+  int up, up_S;         // forward only: the operand is the x2 linear up-sampling (F.interpolate, align_corners=False,
+                        // models/seist.py:566) of a source of up_S samples; the raw ring then holds SOURCE rows
   // shared-memory carve-up (byte offsets from the 128-aligned base)
   int off_raw, off_a, off_b, off_tab_k, off_tab_n, off_red, off_bar, smem_bytes;
 };
@@ -126,24 +128,8 @@ __device__ __forceinline__ void tcc_split(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   lo = x - hi;
 }
-// erf by Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32 rounding level): 1 rcp + 1 ex2 + 7 fma instead of the
-// ~40 instructions of erff - the transform warps are issue-bound on GELU otherwise
-__device__ __forceinline__ float tcc_erf(float z) {
-  const float a = fabsf(z);
-  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * a * a);
-  return copysignf(fmaf(-p * t, e, 1.0f), z);
-}
-__device__ __forceinline__ float tcc_gelu(float x) { return 0.5f * x * (1.0f + tcc_erf(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float tcc_gelu_grad(float x) {
-  const float cdf = 0.5f * (1.0f + tcc_erf(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * exp2f(-0.72134752044448170368f * x * x);
-  return fmaf(x, pdf, cdf);
-}
+__device__ __forceinline__ float tcc_gelu(float x) { return gelu_f(x); }          // common.cuh: fast erf (A&S 7.1.26)
+__device__ __forceinline__ float tcc_gelu_grad(float x) { return gelu_grad_f(x); }
 
 // 16 values per lane -> every lane gets the warp-wide sum of value tcc_red_index(lane) (17 shuffles instead of 80)
 __device__ __forceinline__ float tcc_reduce16(float (&v)[16], int lane) {
@@ -173,6 +159,10 @@ __device__ __forceinline__ int tcc_red_index(int lane) {
       : "r"(taddr)                                                                                                       \
       : "memory");                                                                                                       \
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+
+// first source row staged for a tile whose panel row 0 is up-sampled position p0 (a multiple of 4): the rows needed start at
+// floor((p0 - 1) / 2); TMA boxes must start 16-byte aligned -> rounded down to a multiple of 4
+__device__ __forceinline__ int tcc_up_src0(int p0) { return ((p0 >> 1) - 1) & ~3; }
 
 // dense weight element of the panel B[t][n][c] (grouped convolutions are expanded with zero blocks)
 __device__ __forceinline__ float tcc_wval(const SeistOp& op, int mode, int t, int n, int c) {
@@ -339,7 +329,7 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
               int cv = 0, vi = 0;
               if (c < Kd) vi = resolve_view(op, c, cv);
               else cv = 1 << 20;                    // padded channels: fully out of bounds -> zero fill
-              tcc_tma3(dst0 + boxoff, &maps.m[vi], p0, op.in[vi].c0 + cv, n, bar);
+              tcc_tma3(dst0 + boxoff, &maps.m[vi], g.up ? tcc_up_src0(p0) : p0, op.in[vi].c0 + cv, n, bar);
             } else {
               const int cc = c < Kd ? op.out.c0 + c : (1 << 20);
               int slot = 0;
@@ -396,7 +386,24 @@ __global__ void __launch_bounds__(TCC_NT, 1) tcconv_kernel(const __grid_constant
             const int p = p0 + r;
             const bool inb = act[h] && (r < g.R) && p >= 0 && p < g.src_len;
             const int rr = (act[h] && r < g.Rbox) ? r : 0;
-            if (MODE == 0) {
+            if (MODE == 0 && g.up) {
+              // x2 linear up-sampling of f(source): position p = 2m takes 0.25 f(m-1) + 0.75 f(m), p = 2m+1 takes
+              // 0.75 f(m) + 0.25 f(m+1), clamped at both ends (torch upsample_linear1d, align_corners=False)
+              const int pc = p < 0 ? 0 : p;
+              const int i0 = pc == 0 ? 0 : (pc - 1) >> 1;
+              const int i1 = min(i0 + 1, g.up_S - 1);
+              const float w1 = pc == 0 ? 0.f : ((pc & 1) ? 0.25f : 0.75f);
+              const int s0 = tcc_up_src0(p0);
+              const int a0 = min(max(i0 - s0, 0), g.Rbox - 1), a1 = min(max(i1 - s0, 0), g.Rbox - 1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float f0 = fmaf(e[j].a, raw[j * g.Rbox + a0], e[j].b);
+                float f1 = fmaf(e[j].a, raw[j * g.Rbox + a1], e[j].b);
+                if (F_GELU && e[j].c != 0.f) { f0 = tcc_gelu(f0); f1 = tcc_gelu(f1); }
+                const float v = fmaf(w1, f1 - f0, f0);
+                t[h][j] = (inb && j < nvalid) ? v : 0.f;
+              }
+            } else if (MODE == 0) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float v = fmaf(e[j].a, raw[j * g.Rbox + rr], e[j].b);
@@ -711,8 +718,12 @@ static int tcc_passes() {
 }
 
 bool tcconv_eligible(const SeistOp& op, int mode) {
-  if (op.stride != 1 || op.pool > 1 || op.up_src_L > 0 || op.k > 32) return false;
+  if (op.stride != 1 || op.pool > 1 || op.k > 32) return false;
   if (op.L_in != op.L_out || (op.L_out & 3)) return false;       // TMA: 16-byte row pitch
+  if (op.up_src_L > 0) {     // x2 linear up-sampling folded into the forward transform (the dpk head, models/seist.py:560-566)
+    if (mode != 0 || op.n_in != 1 || op.L_in != 2 * op.up_src_L || (op.up_src_L & 3) || op.in[0].L != op.up_src_L) return false;
+    return (reinterpret_cast<uintptr_t>(op.in[0].x) & 15) == 0;
+  }
   if (op.Cout > 256 || op.Cin > 256) return false;
   if (op.k > 1 && op.p_elem > 0.f) return false;                 // quad-aligned dropout hashing assumes l0 % 4 == 0 rows
   for (int i = 0; i < op.n_in; ++i) {
@@ -741,7 +752,9 @@ static bool tcc_geometry(const SeistOp& op, int mode, TccGeom& g) {
   g.padA = (g.padl + 3) & ~3;
   g.toff = g.padA - g.padl;
   g.R = TCC_M + op.k - 1 + g.toff;
-  g.Rbox = (g.R + 3) & ~3;
+  g.up = (mode == 0 && op.up_src_L > 0) ? 1 : 0;
+  g.up_S = op.up_src_L;
+  g.Rbox = g.up ? ((g.R / 2 + 6 + 3) & ~3) : ((g.R + 3) & ~3);       // raw rows staged per tile (source rows when up-sampling)
   g.Rp = (g.R + 31) & ~31;
   g.N_pad = (g.Nd + 15) & ~15;
   g.passes = tcc_passes();

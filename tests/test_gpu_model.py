@@ -239,3 +239,23 @@ def test_trainer_prefetch_equals_direct_step():
     assert la[2] != la[0]                                  # the parameters really moved
     with pytest.raises(RuntimeError):
         tb.step()                                          # nothing staged
+
+
+@pytest.mark.gpu
+def test_inference_graph_equals_eval_forward():
+    """§8f-4: the captured forward-only plan reproduces model.eval()(x) bit for bit, batch after batch, and equals the golden."""
+    from seist_b200.infer import InferenceGraph
+    g, m = _load("seist_s_dpk")
+    m.eval()
+    x = g["x"].cuda()
+    with torch.no_grad():
+        want = m(x).clone()
+    ig = InferenceGraph(m, x.shape[0], x.shape[2])
+    assert torch.equal(ig(x), want)
+    x2 = torch.roll(x, 1, 0)
+    assert (ig(x2) - torch.roll(want, 1, 0)).abs().max().item() <= 2e-6    # per-waveform independent in eval mode
+    assert torch.equal(ig(x.cpu().pin_memory()).clone(), want)   # pinned host input
+    ref = g["y_eval"]
+    assert (ig(x).cpu() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    with pytest.raises(ValueError):
+        ig(x[:1])
