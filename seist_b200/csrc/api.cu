@@ -103,7 +103,10 @@ static int tcc_mode() {
 }
 static bool tcc_auto(const SeistOp& op, int mode) {
   const int Kd = mode == 0 ? op.Cin : op.Cout, Nd = mode == 0 ? op.Cout : op.Cin;
-  if (op.up_src_L > 0) return mode == 0 && Kd >= 16;     // dpk head: 33 % of the FLOPs, k = 7 / 11 dense taps
+  // dpk head forward (x2 up-sampled operand, k = 7 dense taps): measured wins for the 64->32 and 32->24 layers (0.277 -> 0.191,
+  // 0.274 -> 0.161 ms); 96->64 does not fit its 344 KB of split weights in shared memory (re-staged per tile: 0.438 -> 0.460)
+  // and the 16/24-channel layers at L >= 2048 are transform-bound (gpurun_out/op_times_r2l.json)
+  if (op.up_src_L > 0) return mode == 0 && Kd >= 32 && Kd <= 64;
   if (op.k > 1) return op.L_out <= 512 && Kd >= 8 && Nd >= 8;
   if (mode == 0) return Kd >= 64 && Nd >= 48;
   return Kd >= 96 && Nd >= 96;
