@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SEIST_ABI_VERSION 8
+#define SEIST_ABI_VERSION 9
 #define SEIST_MAX_IN 3
 
 /* ---- BatchNorm table entry (nn.BatchNorm1d, models/seist.py:641) ---------------- */
@@ -185,6 +185,13 @@ typedef struct SeistOp {
   uint64_t zero_bytes;          /* SEIST_OP_ZERO */
   int32_t n_bn;                 /* BN_FINALIZE: entries in bn_table; BN_PREPARE: entries to prepare */
   int32_t bn_lo;                /* BN_PREPARE: first entry                                          */
+  /* lane schedule (seist_plan_run_lanes; seist_b200/schedule.py): the stream this op is issued on, the events
+     (recorded by earlier ops of OTHER lanes) it waits for first, the event it records when done (-1 none) */
+  int32_t lane;
+  int32_t n_wait;
+  int32_t wait_ev[4];
+  int32_t rec_event;
+  int32_t pad1_;
 } SeistOp;
 
 /* ---- entry points ---------------------------------------------------------------------------- */
@@ -206,6 +213,11 @@ int seist_plan_run(const SeistOp* ops, int32_t n, void* stream);
    joined back into `stream` before returning (fork/join, CUDA-graph capturable).  side_stream == NULL
    behaves like seist_plan_run. */
 int seist_plan_run2(const SeistOp* ops, int32_t n, void* stream, void* side_stream);
+
+/* run ops[0..n) on `n_streams` streams by the lane schedule stored in the descriptors: op i is issued on
+   streams[min(lane, n_streams-1)] after waiting for its `wait_ev` events; all lanes are forked from streams[0] at the start
+   and joined back into it at the end (CUDA-graph capturable: the events become graph edges).  */
+int seist_plan_run_lanes(const SeistOp* ops, int32_t n, void* const* streams, int32_t n_streams);
 
 /* BCELoss(weight) with eps inside the logs — models/loss.py:48-56.  preds/targets (N,C,L);
    weight [C]; loss_sum: device double accumulator (zeroed by the call); *loss_out = sum / numel. */

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libseist_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_IN = 3
 MAX_WORLD = 8
 SIG_LANES = 4
@@ -61,6 +61,7 @@ class SeistOp(C.Structure):
         ("heads", C.c_int32), ("p_attn", C.c_float), ("seed_attn", C.c_uint32), ("pad0_", C.c_int32),
         ("comm", C.c_void_p),
         ("zero_bytes", C.c_uint64), ("n_bn", C.c_int32), ("bn_lo", C.c_int32),
+        ("lane", C.c_int32), ("n_wait", C.c_int32), ("wait_ev", C.c_int32 * 4), ("rec_event", C.c_int32), ("pad1_", C.c_int32),
     ]
 
 
@@ -96,6 +97,8 @@ def lib():
     L.seist_op_family.argtypes = [C.c_void_p]
     L.seist_plan_run.restype = C.c_int
     L.seist_plan_run.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.seist_plan_run_lanes.restype = C.c_int
+    L.seist_plan_run_lanes.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
     L.seist_plan_run2.restype = C.c_int
     L.seist_plan_run2.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.seist_bce_fwd.restype = C.c_int
@@ -157,7 +160,7 @@ def lib():
 
 EXPORTS = [
     "seist_abi_version", "seist_sizeof_op", "seist_sizeof_bn", "seist_last_error", "seist_launch_count",
-    "seist_tc_error_flag", "seist_plan_run", "seist_plan_run2", "seist_bce_fwd", "seist_bce_bwd", "seist_huber_fwd", "seist_huber_bwd",
+    "seist_tc_error_flag", "seist_plan_run", "seist_plan_run2", "seist_plan_run_lanes", "seist_bce_fwd", "seist_bce_bwd", "seist_huber_fwd", "seist_huber_bwd",
     "seist_adam_step", "seist_advance_seed", "seist_comm_allreduce", "seist_comm_barrier", "seist_sizeof_comm", "seist_op_family",
     "seist_pick_phase", "seist_detect_event", "seist_pick_counters", "seist_det_counters",
     "seist_normalize", "seist_dpk_labels", "seist_ce_fwd", "seist_ce_bwd",

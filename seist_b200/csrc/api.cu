@@ -240,6 +240,7 @@ static int run_one(const SeistOp& op, cudaStream_t s) {
 extern "C" {
 
 int seist_plan_run(const SeistOp* ops, int32_t n, void* stream);
+const char* seist_last_error(void);
 
 int seist_abi_version(void) { return SEIST_ABI_VERSION; }
 uint64_t seist_sizeof_op(void) { return sizeof(SeistOp); }
@@ -302,6 +303,50 @@ int seist_plan_run2(const SeistOp* ops, int32_t n, void* stream, void* side_stre
   }
   if (forked) return fork_join(side, s, ev);
   return 0;
+}
+
+int seist_plan_run_lanes(const SeistOp* ops, int32_t n, void* const* streams, int32_t n_streams) {
+  if (ops == nullptr || n < 0 || streams == nullptr || n_streams < 1 || n_streams > 8) { seist::set_error("plan_run_lanes: bad arguments"); return -1; }
+  if (n_streams == 1) return seist_plan_run(ops, n, streams[0]);
+  cudaStream_t s0 = (cudaStream_t)streams[0];
+  // events 0 .. n-1: per-op records (ids assigned by the scheduler), n .. n+8: fork / join
+  size_t ev = (size_t)n;
+  for (int l = 1; l < n_streams; ++l) {
+    size_t e = ev;
+    const int fr = fork_join(s0, (cudaStream_t)streams[l], e);      // same fork event slot re-recorded per lane: fine
+    if (fr) return fr;
+  }
+  int rc = 0;
+  for (int i = 0; i < n && rc == 0; ++i) {
+    const SeistOp& op = ops[i];
+    const int lane = op.lane < 0 ? 0 : (op.lane >= n_streams ? n_streams - 1 : op.lane);
+    cudaStream_t s = (cudaStream_t)streams[lane];
+    for (int w = 0; w < op.n_wait && w < 4 && rc == 0; ++w) {
+      if (op.wait_ev[w] < 0 || op.wait_ev[w] >= n) { seist::set_error("plan_run_lanes: bad event id"); rc = -1; break; }
+      cudaEvent_t e = event_at((size_t)op.wait_ev[w]);
+      cudaError_t r = e ? cudaStreamWaitEvent(s, e, 0) : cudaErrorMemoryAllocation;
+      if (r != cudaSuccess) { seist::set_error(cudaGetErrorString(r)); rc = (int)r; }
+    }
+    if (rc) break;
+    rc = seist::run_one(op, s);
+    if (rc != 0) {
+      char buf[600];
+      std::snprintf(buf, sizeof(buf), "op %d (kind %d): %s", i, op.kind, seist_last_error());
+      seist::set_error(buf);
+      break;
+    }
+    if (op.rec_event >= 0) {
+      cudaEvent_t e = op.rec_event < n ? event_at((size_t)op.rec_event) : nullptr;
+      cudaError_t r = e ? cudaEventRecord(e, s) : cudaErrorMemoryAllocation;
+      if (r != cudaSuccess) { seist::set_error(cudaGetErrorString(r)); rc = (int)r; }
+    }
+  }
+  for (int l = 1; l < n_streams; ++l) {          // join (also on errors: never leave a captured fork dangling)
+    size_t e = (size_t)n + 1 + (size_t)l;
+    const int jr = fork_join((cudaStream_t)streams[l], s0, e);
+    if (jr && !rc) rc = jr;
+  }
+  return rc;
 }
 
 int seist_plan_run(const SeistOp* ops, int32_t n, void* stream) {

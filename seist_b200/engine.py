@@ -10,6 +10,7 @@ consuming kernels (reference training/train.py:374 converts every BN to SyncBatc
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -51,6 +52,7 @@ class Engine:
         self.last_plan: Optional[P.Plan] = None
         self.overlap_bwd_w = True
         self._side = {}
+        self._aux = {}
         self.seed_dev: Optional[torch.Tensor] = None     # ONE dropout step counter (device int64) shared by every plan
         self.comm = None                                  # PeerComm (NVLink peer-memory exchange) under data parallelism
 
@@ -155,10 +157,27 @@ class Engine:
             st = self._side[device] = torch.cuda.Stream(device=device)
         return st.cuda_stream
 
+    def _lane_streams(self, device):
+        """[current stream, aux lane (independent branches), weight-gradient lane] as a ctypes array of stream handles."""
+        aux = self._aux.get(device)
+        if aux is None:
+            aux = self._aux[device] = torch.cuda.Stream(device=device, priority=-1)
+        side = self._side.get(device)
+        if side is None:
+            side = self._side[device] = torch.cuda.Stream(device=device)
+        arr = (ctypes.c_void_p * 3)(_stream_ptr(), aux.cuda_stream, side.cuda_stream)
+        return arr
+
     def _run_segments(self, plan: P.Plan, c_ops, segs, stat: torch.Tensor, side: bool = False):
         lib = _lib.lib()
         base = ctypes.addressof(c_ops)
         size = ctypes.sizeof(_lib.SeistOp)
+        if len(segs) == 1 and not segs[0][2] and self.overlap_bwd_w and os.environ.get("SEIST_LANES", "1") != "0":
+            # no host-issued collectives inside the plan: issue it over the lanes the scheduler assigned (schedule.py)
+            streams = self._lane_streams(plan.device)
+            n = segs[0][1] - segs[0][0]
+            _lib.check(lib.seist_plan_run_lanes(base + segs[0][0] * size, n, streams, 3), "seist_plan_run_lanes")
+            return
         side_ptr = self._side_stream(plan.device) if side else 0
         for start, end, sync in segs:
             i = 0

@@ -772,6 +772,9 @@ def to_c(plan: Plan, ops: List[Op]):
             c.n_bn, c.bn_lo = op.n_bn, op.bn_lo
             if plan.comm is not None and op.sync_bn:
                 c.comm = plan.comm.dev_ptr          # statistic sum over NVLink peer memory fused into this kernel
+    from .schedule import schedule_lanes
+    info = schedule_lanes(plan, ops, arr)           # lane / event fields (used by seist_plan_run_lanes only)
+    plan.lane_info = getattr(plan, "lane_info", []) + [info]
     return arr
 
 
