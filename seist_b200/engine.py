@@ -172,8 +172,11 @@ class Engine:
         lib = _lib.lib()
         base = ctypes.addressof(c_ops)
         size = ctypes.sizeof(_lib.SeistOp)
-        if len(segs) == 1 and not segs[0][2] and self.overlap_bwd_w and os.environ.get("SEIST_LANES", "1") != "0":
-            # no host-issued collectives inside the plan: issue it over the lanes the scheduler assigned (schedule.py)
+        if (len(segs) == 1 and not segs[0][2] and plan.comm is None and self.overlap_bwd_w
+                and os.environ.get("SEIST_LANES", "1") != "0"):
+            # single GPU: issue the plan over the lanes the scheduler assigned (schedule.py).  Data-parallel plans stay on
+            # one main stream: their BN_PREPARE kernels pair up across ranks by an epoch counter, so every rank must run
+            # them in the same order, which only stream order guarantees.
             streams = self._lane_streams(plan.device)
             n = segs[0][1] - segs[0][0]
             _lib.check(lib.seist_plan_run_lanes(base + segs[0][0] * size, n, streams, 3), "seist_plan_run_lanes")

@@ -542,3 +542,51 @@ def test_fused_peer_exchange_two_virtual_ranks_equal_single_rank():
     for p in plans:
         assert (p.flat.RB - p1.flat.RB).abs().max().item() <= 1e-5 * (p1.flat.RB.abs().max().item() + 1e-3)
         assert torch.equal(p.stat, plans[0].stat) and torch.equal(p.gstat, plans[0].gstat)
+
+
+# ------------------------------------------------------------------------------------------------
+# several consecutive steps: the fused step (graph replay: seed advance, forward, BCE, backward, Adam, CyclicLR) against
+# the oracle restatement driven by torch.optim.Adam + torch's CyclicLR in the reference's step order (train.py:87-116)
+# ------------------------------------------------------------------------------------------------
+def test_five_step_trajectory_matches_oracle():
+    from seist_b200.train import Trainer, make_cyclic_lr
+    name, N, L, steps = "seist_s_dpk", 4, 2048, 5
+    base = randomize(create_model(name, in_channels=3, in_samples=L), seed=13)
+    base.set_drop_rates(**ZERO_DROPS)
+    sd0 = {k: v.clone() for k, v in base.state_dict().items()}
+    x, tgt = R.synth_waveforms(N, L, seed=31)
+    # oracle trajectory
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+          for k, v in sd0.items()}
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=8e-5)
+    sched = torch.optim.lr_scheduler.CyclicLR(opt, base_lr=8e-5, max_lr=1e-3, step_size_up=2000, step_size_down=3000,
+                                              mode="exp_range", gamma=8e-5 ** (1 / 2000), cycle_momentum=False)
+    ref_losses = []
+    for _ in range(steps):
+        y, bufs = R.forward(sd, x, R.spec_for(name), training=True)
+        loss = R.bce_loss(y, tgt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        sched.step()
+        for k, b in bufs.items():
+            sd[k] = b
+        ref_losses.append(loss.item())
+    # fused trajectory
+    m = create_model(name, in_channels=3, in_samples=L)
+    m.load_state_dict(sd0)
+    m.set_drop_rates(**ZERO_DROPS)
+    m.cuda()
+    tr = Trainer(m, lr_schedule=make_cyclic_lr(1000))
+    got = [float(tr.step(x.cuda(), tgt.cuda())) for _ in range(steps)]
+    for a, b in zip(got, ref_losses):
+        assert abs(a - b) <= 2e-3 * abs(b), (got, ref_losses)
+    assert got[-1] != got[0]
+    # BatchNorm running statistics after 5 steps (momentum accumulation) and the parameters themselves
+    sdm = m.state_dict()
+    for k, v in sd.items():
+        if "running_" in k:
+            assert (sdm[k].cpu() - v).abs().max().item() <= 2e-3 * (v.abs().max().item() + 1e-3), k
+        if k.endswith("num_batches_tracked"):
+            assert int(sdm[k]) == int(v) == steps
