@@ -66,6 +66,11 @@ int tcconv_error_flag();
 // (tests/test_gpu_ops.py::test_tcgen05_kernels_match_interpreter) but, since the SIMT kernels moved to FFMA2 and
 // 4 CTAs/SM, slower than them on every op of the model family (profiles/r1_tc_vs_simt.txt) - opt-in:
 // SEIST_TC=1 every eligible op, SEIST_TC=2 the former heuristic (GELU-input / wide contractions), default never.
+// integer tuning knob, read from the environment on every call (launch time only; graphs replay the captured choice)
+int env_knob(const char* name, int def) {
+  const char* e = std::getenv(name);
+  return (e && *e) ? std::atoi(e) : def;
+}
 int bww_waves() {
   static int v = -1;
   if (v < 0) { const char* e = std::getenv("SEIST_BWW_WAVES"); v = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 2; }

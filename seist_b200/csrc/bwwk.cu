@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(BK_NT, (K <= 9 && NPR == 2) ? 3 : 2) bwwk_kern
   float* in_s = g_s + (CO_B / 2) * gpitch;                // [CI_B][pitch]
   BkOut* oc_s = reinterpret_cast<BkOut*>(g_s + area_f);   // [CO_B]
   float* src_s = reinterpret_cast<float*>(oc_s + CO_B);   // [CI_B][width+4] (up-sampled input only)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int co_base = grp * gs_out + (blockIdx.y - grp * tpg) * CO_B;
   const int ci_lo = grp * gs_in + blockIdx.z * CI_B;
   const int nci = min(CI_B, Cin_hi - ci_lo);
@@ -98,6 +98,13 @@ __global__ void __launch_bounds__(BK_NT, (K <= 9 && NPR == 2) ? 3 : 2) bwwk_kern
     const int n = tile / chunks_per_n;
     const int l0 = (tile - n * chunks_per_n) * PC;
     const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
+    // ---- conv-input rows: in_s[r][pos] <-> conv-input coordinate p_base + pos.  Plain rows are copied raw and
+    // asynchronously FIRST (their latency hides behind the gacc loads) and transformed in place below
+    const int p_base = l0 * S - op.pad_left;
+    if (op.up_src_L == 0) {
+      rows_issue_plain(op, n, ci_lo, nci, nci, in_s, pitch, width, p_base);
+      cp_async_commit();
+    }
     // ---- gacc rows, interleaved in channel pairs: g_s[pr][2*s + half] ---------------------------------
     for (int idx = tid; idx < (CO_B / 2) * QPR; idx += BK_NT) {
       const int pr = idx / QPR, q = idx - pr * QPR;
@@ -146,32 +153,11 @@ __global__ void __launch_bounds__(BK_NT, (K <= 9 && NPR == 2) ? 3 : 2) bwwk_kern
       bk_st4(gp, make_float4(gh[0].x, gh[1].x, gh[0].y, gh[1].y));
       bk_st4(gp + 4, make_float4(gh[0].z, gh[1].z, gh[0].w, gh[1].w));
     }
-    // ---- conv-input rows: in_s[r][pos] <-> conv-input coordinate p_base + pos ----------------------
-    const int p_base = l0 * S - op.pad_left;
     if (op.up_src_L > 0) {
       stage_upsampled_rows(op, n, ci_lo, nci, in_s, pitch, width, p_base, src_s, width + 4, Lsrc, ratio);
     } else {
-      for (int r = warp; r < nci; r += BK_NT / 32) {
-        const RowSrc rs = make_row(op, n, ci_lo + r);
-        float* dst = in_s + r * pitch;
-        for (int pos0 = lane; pos0 < width; pos0 += 32 * 4) {
-          float v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int p = p_base + pos0 + 32 * u;
-            v[u] = (pos0 + 32 * u < width && p >= 0 && p < op.L_in) ? rs.x[p] : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int pos = pos0 + 32 * u, p = p_base + pos;
-            if (pos < width) {
-              float t = fmaf(rs.sc, v[u], rs.sh);
-              if (rs.act == SEIST_ACT_GELU) t = gelu_f(t);
-              dst[pos] = (p >= 0 && p < op.L_in) ? t : 0.f;
-            }
-          }
-        }
-      }
+      cp_async_wait<0>();
+      rows_transform_plain(op, n, ci_lo, nci, in_s, pitch, width, p_base);
     }
     __syncthreads();
     // ---- accumulate -------------------------------------------------------------------------------

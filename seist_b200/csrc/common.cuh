@@ -14,6 +14,7 @@ namespace seist {
 // ---- launch bookkeeping (api.cu) -------------------------------------------------------------
 void note_launch();
 int bww_waves();   // resident CTAs per SM the persistent weight-gradient kernels are sized for (SEIST_BWW_WAVES, default 2)
+int env_knob(const char* name, int def);   // integer tuning knob from the environment (measurement only)
 int check_launch(const char* what);
 void set_error(const char* msg);
 
@@ -54,6 +55,25 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return fmaf(x, pdf, cdf);
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// ---- asynchronous global -> shared copies (LDGSTS) ---------------------------------------------------------------------
+// Staging loops of the form "load, transform, store to shared" expose one memory latency per iteration unless the compiler
+// can batch the loads (it cannot across the conditional GELU); ncu showed 35-50 % of the stall samples of the weight-
+// gradient / k-tap kernels on the first use of such a load.  The kernels therefore copy the RAW operands with cp.async
+// (every copy of a tile in flight at once, no registers held) and the issuing thread transforms its own elements in place
+// after cp.async.wait_group (which orders a thread's own copies: no barrier between copy and transform).
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -64,16 +64,58 @@ __device__ __forceinline__ RowSrc make_row(const SeistOp& op, int n, int ci) {
 
 
 
-// Two-phase staging of linearly up-sampled rows (reference F.interpolate(mode="linear"), models/seist.py:566):
-// phase 1 evaluates BN/GELU once per SOURCE sample into `src_s`, phase 2 interpolates from shared memory, so
-// the activation is not re-evaluated for both neighbours of every up-sampled sample.  Must be called by all
-// threads of the CTA (contains a barrier).  dst[r*pitch + pos] <-> conv-input coordinate p_base + pos.
-__device__ __forceinline__ void stage_upsampled_rows(const SeistOp& op, int n, int ci0, int nrows, float* dst, int pitch,
-                                                     int width, int p_base, float* src_s, int spitch, int Lsrc,
-                                                     float ratio) {
+// ------------------------------------------------------------------------------------------------
+// Asynchronous staging of conv-input rows.  dst[r*pitch + pos] <-> conv-input coordinate p_base + pos of channel
+// ci0 + r.  Element ownership (row = warp + k*nwarps, pos = lane + 32*u) is the same in the issue and the transform
+// function, so a thread only ever touches elements it copied itself.
+// ------------------------------------------------------------------------------------------------
+// raw copies of the valid range, zeros in the padding and in rows >= nrows (up to nrows_pad)
+__device__ __forceinline__ void rows_issue_plain(const SeistOp& op, int n, int ci0, int nrows, int nrows_pad, float* dst,
+                                                 int pitch, int width, int p_base) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < nrows_pad; r += nwarps) {
+    float* d = dst + r * pitch;
+    if (r >= nrows) {
+      for (int pos = lane; pos < width; pos += 32) d[pos] = 0.f;
+      continue;
+    }
+    int cv;
+    const int vi = resolve_view(op, ci0 + r, cv);
+    const float* xr = view_row(op.in[vi], n, cv);
+    const uint32_t da = smem_addr(d);
+    for (int pos = lane; pos < width; pos += 32) {
+      const int p = p_base + pos;
+      if (p >= 0 && p < op.L_in) cp_async4(da + 4 * pos, xr + p);
+      else d[pos] = 0.f;
+    }
+  }
+}
+// BN-apply / GELU of the consumer view, in place, after cp_async_wait<0>()
+__device__ __forceinline__ void rows_transform_plain(const SeistOp& op, int n, int ci0, int nrows, float* dst, int pitch,
+                                                     int width, int p_base) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int pos_lo = max(0, -p_base), pos_hi = min(width, op.L_in - p_base);   // valid positions [pos_lo, pos_hi)
+  for (int r = warp; r < nrows; r += nwarps) {
+    const RowSrc rs = make_row(op, n, ci0 + r);
+    if (rs.act == SEIST_ACT_NONE && rs.sc == 1.f && rs.sh == 0.f) continue;
+    float* d = dst + r * pitch;
+    if (rs.act == SEIST_ACT_GELU) {
+      for (int pos = lane; pos < pos_hi; pos += 32)
+        if (pos >= pos_lo) d[pos] = gelu_f(fmaf(rs.sc, d[pos], rs.sh));
+    } else {
+      for (int pos = lane; pos < pos_hi; pos += 32)
+        if (pos >= pos_lo) d[pos] = fmaf(rs.sc, d[pos], rs.sh);
+    }
+  }
+}
+
+// source window of the linearly up-sampled rows: conv-input coordinates [p_base, p_base + width) read the source
+// samples [i_lo, i_lo + count)
+__device__ __forceinline__ void upsample_window(const SeistOp& op, int p_base, int width, int spitch, int Lsrc, float ratio,
+                                                int& i_lo, int& count) {
   const int p_lo = max(p_base, 0), p_hi = min(p_base + width - 1, op.L_in - 1);
-  int i_lo = 0, count = 0;
+  i_lo = 0;
+  count = 0;
   if (p_hi >= p_lo) {
     int a0, a1, b0, b1;
     float lam;
@@ -82,11 +124,33 @@ __device__ __forceinline__ void stage_upsampled_rows(const SeistOp& op, int n, i
     i_lo = a0;
     count = min(b1 - a0 + 1, spitch);
   }
+}
+__device__ __forceinline__ void src_issue(const SeistOp& op, int n, int ci0, int nrows, float* src_s, int spitch, int i_lo,
+                                          int count) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < nrows; r += nwarps) {
+    int cv;
+    const int vi = resolve_view(op, ci0 + r, cv);
+    const float* xr = view_row(op.in[vi], n, cv) + i_lo;
+    const uint32_t da = smem_addr(src_s + r * spitch);
+    for (int i = lane; i < count; i += 32) cp_async4(da + 4 * i, xr + i);
+  }
+}
+__device__ __forceinline__ void src_transform(const SeistOp& op, int n, int ci0, int nrows, float* src_s, int spitch, int count) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int r = warp; r < nrows; r += nwarps) {
     const RowSrc rs = make_row(op, n, ci0 + r);
-    for (int i = lane; i < count; i += 32) src_s[r * spitch + i] = row_u(rs, i_lo + i);
+    float* d = src_s + r * spitch;
+    if (rs.act == SEIST_ACT_GELU) {
+      for (int i = lane; i < count; i += 32) d[i] = gelu_f(fmaf(rs.sc, d[i], rs.sh));
+    } else if (rs.sc != 1.f || rs.sh != 0.f) {
+      for (int i = lane; i < count; i += 32) d[i] = fmaf(rs.sc, d[i], rs.sh);
+    }
   }
-  __syncthreads();
+}
+__device__ __forceinline__ void rows_interpolate(const SeistOp& op, int nrows, float* dst, int pitch, int width, int p_base,
+                                                 const float* src_s, int spitch, int i_lo, int Lsrc, float ratio) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int r = warp; r < nrows; r += nwarps) {
     const float* sr = src_s + r * spitch;
     float* d = dst + r * pitch;
@@ -102,6 +166,23 @@ __device__ __forceinline__ void stage_upsampled_rows(const SeistOp& op, int n, i
       d[pos] = v;
     }
   }
+}
+
+// Two-phase staging of linearly up-sampled rows (reference F.interpolate(mode="linear"), models/seist.py:566):
+// phase 1 brings the SOURCE samples in (asynchronous copies, all in flight at once) and evaluates BN/GELU once per
+// source sample in place, phase 2 interpolates from shared memory, so the activation is not re-evaluated for both
+// neighbours of every up-sampled sample.  Must be called by all threads of the CTA (contains a barrier).
+__device__ __forceinline__ void stage_upsampled_rows(const SeistOp& op, int n, int ci0, int nrows, float* dst, int pitch,
+                                                     int width, int p_base, float* src_s, int spitch, int Lsrc,
+                                                     float ratio) {
+  int i_lo, count;
+  upsample_window(op, p_base, width, spitch, Lsrc, ratio, i_lo, count);
+  src_issue(op, n, ci0, nrows, src_s, spitch, i_lo, count);
+  cp_async_commit();
+  cp_async_wait<0>();
+  src_transform(op, n, ci0, nrows, src_s, spitch, count);
+  __syncthreads();
+  rows_interpolate(op, nrows, dst, pitch, width, p_base, src_s, spitch, i_lo, Lsrc, ratio);
 }
 
 }  // namespace seist

@@ -9,6 +9,7 @@
 // registers).  The same engine run with flipped/transposed weights over the BN-backward-combined output
 // gradient is the data gradient (stride 1).  The weight gradient keeps lanes on the sample axis: a warp
 // owns a (4 co) x (TCI ci) x K tile of dW in registers and reduces it over lanes once per CTA lifetime.
+#include <algorithm>
 #include "common.cuh"
 #include "conv_common.cuh"
 
@@ -54,46 +55,24 @@ __device__ __forceinline__ void ck_accumulate(const float* irow, const float* wr
   }
 }
 
-// stage rows of the consumer view (conv-input coordinates p_base .. p_base + width) — 8 loads in flight
-__device__ __forceinline__ void ck_stage_input(const SeistOp& op, int n, int ci0, int cic, float* in_s, int pitch,
-                                               int width, int p_base, int Lsrc, float ratio) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool plain = op.up_src_L == 0;
-  for (int r = warp; r < CK_CIC; r += CK_NT / 32) {
-    float* dst = in_s + r * pitch;
-    if (r >= cic) {
-      for (int pos = lane; pos < width; pos += 32) dst[pos] = 0.f;
-      continue;
-    }
-    const RowSrc rs = make_row(op, n, ci0 + r);
-    if (plain) {
-      for (int pos0 = lane; pos0 < width; pos0 += 32 * 8) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int p = p_base + pos0 + 32 * u;
-          v[u] = (pos0 + 32 * u < width && p >= 0 && p < op.L_in) ? rs.x[p] : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int pos = pos0 + 32 * u, p = p_base + pos;
-          if (pos < width) {
-            float t = fmaf(rs.sc, v[u], rs.sh);
-            if (rs.act == SEIST_ACT_GELU) t = gelu_f(t);
-            dst[pos] = (p >= 0 && p < op.L_in) ? t : 0.f;
-          }
-        }
-      }
-    } else {
-      for (int pos = lane; pos < width; pos += 32) dst[pos] = conv_input_at(op, rs, p_base + pos, Lsrc, ratio);
-    }
+// weights of one reduction chunk, [r][t][col] (zero padded), asynchronous 4-byte gathers
+template <int K>
+__device__ __forceinline__ void ck_issue_weights_fwd(const SeistOp& op, float* w_s, int CO_B, int co_base, int co_end, int gs_in,
+                                                     int ci0, int cic) {
+  const uint32_t wa = smem_addr(w_s);
+  for (int idx = threadIdx.x; idx < CK_CIC * K * CO_B; idx += CK_NT) {
+    const int col = idx % CO_B, rest = idx / CO_B;
+    const int t = rest % K, r = rest / K;
+    const int co = co_base + col;
+    if (r < cic && co < co_end) cp_async4(wa + 4 * idx, op.W + ((size_t)co * gs_in + ci0 + r) * K + t);
+    else w_s[idx] = 0.f;
   }
 }
 
 // ================================================================================================
 // forward
 // ================================================================================================
-template <int K, int S>
+template <int K, int S, int NBUF>
 __global__ void __launch_bounds__(CK_NT, 3) convk_fwd_kernel(const __grid_constant__ SeistOp op, const int WC) {
   extern __shared__ __align__(16) float ck_smem[];
   const int WP = 8 / WC, CO_B = 8 * WC, TLo = 128 * WP;
@@ -107,13 +86,21 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_fwd_kernel(const __grid_consta
   const int ci_grp = grp * gs_in;
   const int width = TLo * S + K - S;
   const int pitch = ((width + 3) & ~3) + 4;
-  float* in_s = ck_smem;                               // [CIC][pitch]
-  float* w_s = ck_smem + CK_CIC * pitch;               // [CIC][K][CO_B]
-  float* red_s = w_s + CK_CIC * K * CO_B;              // [8 warps][16]
-  float* src_s = red_s + 8 * 16;                       // [CIC][width+4] (up-sampled input only)
+  // Shared memory: raw operands of reduction chunk c + 1 are copied asynchronously while chunk c is being accumulated
+  // (NBUF == 2: plain rows are double buffered and transformed in place; up-sampled rows double buffer the SOURCE window
+  // and interpolate into the single in_s); NBUF == 1 where two stages do not fit: copies of a chunk all in flight at once.
+  const bool up = op.up_src_L > 0;
+  const int spitch = width + 4;
+  const int in_f = CK_CIC * pitch, w_f = CK_CIC * K * CO_B, src_f = up ? CK_CIC * spitch : 0;
+  float* red_s = ck_smem;                              // [8 warps][16]
+  float* in_s = ck_smem + 8 * 16;                      // [NBUF (1 if up)][CIC][pitch]
+  float* w_s = in_s + (up ? 1 : NBUF) * in_f;          // [NBUF][CIC][K][CO_B]
+  float* src_s = w_s + NBUF * w_f;                     // [NBUF][CIC][width+4] (up-sampled input only)
   const int Lsrc = op.in[0].L;
-  const float ratio = op.up_src_L > 0 ? (float)Lsrc / (float)op.L_in : 1.f;
+  const float ratio = up ? (float)Lsrc / (float)op.L_in : 1.f;
   const int p_base = l0 * S - op.pad_left;
+  int i_lo = 0, count = 0;
+  if (up) upsample_window(op, p_base, width, spitch, Lsrc, ratio, i_lo, count);
 
   float2 acc[4][4];
 #pragma unroll
@@ -121,26 +108,34 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_fwd_kernel(const __grid_consta
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[c][j] = make_float2(0.f, 0.f);
 
-  for (int ci0 = 0; ci0 < gs_in; ci0 += CK_CIC) {
-    const int cic = min(CK_CIC, gs_in - ci0);
-    if (op.up_src_L > 0) {
-      stage_upsampled_rows(op, n, ci_grp + ci0, cic, in_s, pitch, width, p_base, src_s, width + 4, Lsrc, ratio);
-      for (int r = cic + warp; r < CK_CIC; r += CK_NT / 32)
-        for (int pos = lane; pos < width; pos += 32) in_s[r * pitch + pos] = 0.f;
-    } else {
-      ck_stage_input(op, n, ci_grp + ci0, cic, in_s, pitch, width, p_base, Lsrc, ratio);
+  const int nchunks = (gs_in + CK_CIC - 1) / CK_CIC;
+  auto issue = [&](int c) {
+    const int b = (NBUF == 2) ? (c & 1) : 0;
+    const int ci0 = c * CK_CIC, cic = min(CK_CIC, gs_in - ci0);
+    if (up) src_issue(op, n, ci_grp + ci0, cic, src_s + b * src_f, spitch, i_lo, count);
+    else rows_issue_plain(op, n, ci_grp + ci0, cic, cic, in_s + b * in_f, pitch, width, p_base);
+    ck_issue_weights_fwd<K>(op, w_s + b * w_f, CO_B, co_base, co_end, gs_in, ci0, cic);
+    cp_async_commit();
+  };
+  if (NBUF == 2) issue(0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int b = (NBUF == 2) ? (c & 1) : 0;
+    const int ci0 = c * CK_CIC, cic = min(CK_CIC, gs_in - ci0);
+    if (NBUF == 1) issue(c);
+    cp_async_wait<0>();
+    if (up) src_transform(op, n, ci_grp + ci0, cic, src_s + b * src_f, spitch, count);
+    else rows_transform_plain(op, n, ci_grp + ci0, cic, in_s + b * in_f, pitch, width, p_base);
+    __syncthreads();                                   // chunk c is staged; everybody is done with chunk c - 1
+    if (NBUF == 2 && c + 1 < nchunks) issue(c + 1);
+    const float* in_c = up ? in_s : in_s + b * in_f;
+    if (up) {
+      rows_interpolate(op, cic, in_s, pitch, width, p_base, src_s + b * src_f, spitch, i_lo, Lsrc, ratio);
+      __syncthreads();
     }
-    for (int idx = tid; idx < CK_CIC * K * CO_B; idx += CK_NT) {
-      const int col = idx % CO_B, rest = idx / CO_B;
-      const int t = rest % K, r = rest / K;
-      const int co = co_base + col;
-      w_s[idx] = (r < cic && co < co_end) ? op.W[((size_t)co * gs_in + ci0 + r) * K + t] : 0.f;
-    }
-    __syncthreads();
-    const float* ib = in_s + (wp * 128 + 4 * lane) * S;
-    const float* wb = w_s + wc * 8;
+    const float* ib = in_c + (wp * 128 + 4 * lane) * S;
+    const float* wb = w_s + b * w_f + wc * 8;
     for (int r = 0; r < cic; ++r) ck_accumulate<K, S>(ib + r * pitch, wb + r * K * CO_B, CO_B, acc);
-    __syncthreads();
+    if (NBUF == 1) __syncthreads();
   }
 
   // ---- epilogue ----------------------------------------------------------------------------------
@@ -223,8 +218,8 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_fwd_kernel(const __grid_consta
 //     channels per warp = 4 input channels x 2 parities, and a thread that owns 4 consecutive u writes 8
 //     consecutive input samples per channel.
 // ================================================================================================
-template <int K, int S>
-__global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_constant__ SeistOp op, const int WC) {
+template <int K, int S, int NBUF>
+__global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_constant__ SeistOp op, const int WC, const int NRAW) {
   extern __shared__ __align__(16) float ck_smem[];
   constexpr int KE = S == 2 ? (K + 1) / 2 : K;          // taps of the stride-1 engine
   constexpr int CPW = S == 2 ? 4 : 8;                   // real input channels per warp
@@ -239,12 +234,21 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_c
   const int co_grp = grp * gs_out;
   const int width = TLo + KE - 1;
   const int pitch = ((width + 3) & ~3) + 4;
-  float* z_s = ck_smem;                                // [CIC][pitch]
-  float* w_s = ck_smem + CK_CIC * pitch;               // [CIC][KE][VC_B]
-  float* red_s = w_s + CK_CIC * KE * VC_B;             // [8][16]
+  // Shared memory: the raw operands of the output-gradient rows (du | x | dxd as the op needs them: NRAW planes) of
+  // chunk c + 1 are copied asynchronously while chunk c is accumulated (NBUF == 2), and combined IN PLACE into plane 0
+  // (BN backward, sigmoid', drop factors) by the thread that copied them.
+  const bool has_bn = (op.out.bn >= 0 && op.out.g != nullptr);
+  const bool need_x = has_bn || op.out_act == SEIST_OUT_SIGMOID;
+  const int z_f = CK_CIC * pitch, w_f = CK_CIC * KE * VC_B;
+  float* red_s = ck_smem;                              // [8][16]
+  float* z_s = ck_smem + 8 * 16;                       // [NBUF][NRAW][CIC][pitch]
+  float* w_s = z_s + NBUF * NRAW * z_f;                // [NBUF][CIC][KE][VC_B]
   const uint64_t seed = load_seed(op.step_seed);
   const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
   const int m_base = p0 + op.pad_left / S - (KE - 1);  // output-sample coordinate of z_s[.][0]
+  const int pos_lo = max(0, -m_base), pos_hi = min(width, op.L_out - m_base);   // valid positions [pos_lo, pos_hi)
+  const float* src0 = has_bn ? op.out.g : op.out_dxd;  // plane 0 (nullptr: zeros)
+  const float* src2 = has_bn ? op.out_dxd : nullptr;   // plane 2
 
   float2 acc[4][4];
 #pragma unroll
@@ -252,47 +256,81 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_c
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[c][j] = make_float2(0.f, 0.f);
 
-  for (int co0 = 0; co0 < gs_out; co0 += CK_CIC) {
-    const int coc = min(CK_CIC, gs_out - co0);
-    for (int r = warp; r < CK_CIC; r += CK_NT / 32) {
-      float* dst = z_s + r * pitch;
-      if (r >= coc) {
-        for (int pos = lane; pos < width; pos += 32) dst[pos] = 0.f;
-        continue;
-      }
-      const int co = co_grp + co0 + r;
-      const OutGradCoef kc = out_grad_coef(op, co);
-      for (int pos0 = lane; pos0 < width; pos0 += 32 * 4) {
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int pos = pos0 + 32 * u, m = m_base + pos;
-          v[u] = (pos < width && m >= 0 && m < op.L_out) ? out_grad_at(op, kc, n, co, m) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int pos = pos0 + 32 * u, m = m_base + pos;
-          if (pos < width) {
-            float t = v[u] * pf;
-            if (op.p_elem > 0.f && m >= 0 && m < op.L_out) t *= elem_factor(op, seed, n, co, m);
-            dst[pos] = t;
-          }
+  const int nchunks = (gs_out + CK_CIC - 1) / CK_CIC;
+  auto issue = [&](int c) {
+    const int b = (NBUF == 2) ? (c & 1) : 0;
+    const int co0 = c * CK_CIC, coc = min(CK_CIC, gs_out - co0);
+    float* zb = z_s + b * NRAW * z_f;
+    for (int r = warp; r < coc; r += CK_NT / 32) {
+      const size_t row = ((size_t)n * op.out.Ct + op.out.c0 + co_grp + co0 + r) * (size_t)op.out.L + m_base;
+      float* d = zb + r * pitch;
+      const uint32_t da = smem_addr(d);
+      for (int pos = lane; pos < width; pos += 32) {
+        if (pos >= pos_lo && pos < pos_hi) {
+          if (src0) cp_async4(da + 4 * pos, src0 + row + pos);
+          else d[pos] = 0.f;
+          if (need_x) cp_async4(da + 4 * (z_f + pos), op.out.x + row + pos);
+          if (src2) cp_async4(da + 4 * (2 * z_f + pos), src2 + row + pos);
+        } else {
+          d[pos] = 0.f;
         }
       }
     }
     // flipped + transposed weights: w_s[(r*KE + tf)*VC_B + col] = W[co0+r][ci(col)][t(tf, parity(col))]
+    float* wb = w_s + b * w_f;
+    const uint32_t wa = smem_addr(wb);
     for (int idx = tid; idx < CK_CIC * KE * VC_B; idx += CK_NT) {
       const int col = idx % VC_B, rest = idx / VC_B;
       const int tf = rest % KE, r = rest / KE;
       const int ci = ci_base + (S == 2 ? (col >> 1) : col);
       const int t = S == 2 ? (col & 1) + 2 * (KE - 1 - tf) : (K - 1 - tf);
-      w_s[idx] = (r < coc && ci < ci_end && t < K) ? op.W[((size_t)(co_grp + co0 + r) * gs_in + (ci - grp * gs_in)) * K + t] : 0.f;
+      if (r < coc && ci < ci_end && t < K)
+        cp_async4(wa + 4 * idx, op.W + ((size_t)(co_grp + co0 + r) * gs_in + (ci - grp * gs_in)) * K + t);
+      else
+        wb[idx] = 0.f;
     }
-    __syncthreads();
-    const float* zb = z_s + wp * 128 + 4 * lane;
-    const float* wb = w_s + wc * 8;
+    cp_async_commit();
+  };
+  auto combine = [&](int c) {
+    const int b = (NBUF == 2) ? (c & 1) : 0;
+    const int co0 = c * CK_CIC, coc = min(CK_CIC, gs_out - co0);
+    float* zb = z_s + b * NRAW * z_f;
+    const bool scale_only = !need_x;
+    if (scale_only && pf == 1.f && op.p_elem <= 0.f) return;   // plane 0 already holds the gradient
+    for (int r = warp; r < coc; r += CK_NT / 32) {
+      const int co = co_grp + co0 + r;
+      const OutGradCoef kc = out_grad_coef(op, co);
+      float* d = zb + r * pitch;
+      for (int pos = lane; pos < pos_hi; pos += 32) {
+        if (pos < pos_lo) continue;
+        float g = d[pos];
+        if (need_x) {
+          const float x = d[z_f + pos];
+          if (has_bn) {
+            g = fmaf(kc.A, g, fmaf(kc.Bx, x, kc.Cc));
+            if (src2) g += d[2 * z_f + pos];
+          }
+          if (op.out_act == SEIST_OUT_SIGMOID) g *= x * (1.0f - x);
+        }
+        g *= pf;
+        if (op.p_elem > 0.f) g *= elem_factor(op, seed, n, co, m_base + pos);
+        d[pos] = g;
+      }
+    }
+  };
+  if (NBUF == 2) issue(0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int b = (NBUF == 2) ? (c & 1) : 0;
+    const int coc = min(CK_CIC, gs_out - c * CK_CIC);
+    if (NBUF == 1) issue(c);
+    cp_async_wait<0>();
+    combine(c);
+    __syncthreads();                                   // chunk c is staged; everybody is done with chunk c - 1
+    if (NBUF == 2 && c + 1 < nchunks) issue(c + 1);
+    const float* zb = z_s + b * NRAW * z_f + wp * 128 + 4 * lane;
+    const float* wb = w_s + b * w_f + wc * 8;
     for (int r = 0; r < coc; ++r) ck_accumulate<KE, 1>(zb + r * pitch, wb + r * KE * VC_B, VC_B, acc);
-    __syncthreads();
+    if (NBUF == 1) __syncthreads();
   }
 
   // ---- route to the source view ----------------------------------------------------------------------
@@ -517,17 +555,37 @@ static int ck_set_smem(Kf kernel, size_t bytes) {
 
 static int pick_wc(int channels) { return channels > 32 ? 8 : (channels > 16 ? 4 : (channels > 8 ? 2 : 1)); }
 
+// two stages (asynchronous prefetch of the next reduction chunk) where they do not cost a resident CTA below 2 per SM
+static int ck_pick_nbuf(size_t bytes1, size_t bytes2) {
+  const int knob = env_knob("SEIST_CK_NBUF", 0);
+  if (knob == 1 || knob == 2) return bytes2 > 220 * 1024 ? 1 : knob;
+  // measured on B200 (gpurun sweep_b): the second stage costs a resident CTA on most layers of the model family and
+  // loses more than the prefetch wins (convk_fwd 4.16 -> 4.46 ms, convk_bwd_data 4.77 -> 4.89 ms per step): two stages
+  // only where they are free
+  auto ctas = [](size_t b) { return (int)std::min<size_t>(3, (227 * 1024) / (b + 1024)); };
+  return (ctas(bytes2) >= ctas(bytes1) && bytes2 <= 220 * 1024) ? 2 : 1;
+}
+
 template <int K, int S>
 static int launch_fwd_ks(const SeistOp& op, cudaStream_t s) {
   const int gs_out = op.Cout / op.groups;
   const int WC = pick_wc(gs_out), WP = 8 / WC, CO_B = 8 * WC, TLo = 128 * WP;
   const int width = TLo * S + K - S, pitch = ((width + 3) & ~3) + 4;
-  const size_t smem = sizeof(float) * ((size_t)CK_CIC * pitch + (size_t)CK_CIC * K * CO_B + 8 * 16 +
-                                       (op.up_src_L > 0 ? (size_t)CK_CIC * (width + 4) : 0));
+  const bool up = op.up_src_L > 0;
+  const size_t in_f = (size_t)CK_CIC * pitch, w_f = (size_t)CK_CIC * K * CO_B, src_f = up ? (size_t)CK_CIC * (width + 4) : 0;
+  auto bytes = [&](int nbuf) { return sizeof(float) * (8 * 16 + (up ? 1 : nbuf) * in_f + nbuf * (w_f + src_f)); };
+  const int nbuf = ck_pick_nbuf(bytes(1), bytes(2));
+  const size_t smem = bytes(nbuf);
   dim3 grid((op.L_out + TLo - 1) / TLo, op.N, op.groups * ((gs_out + CO_B - 1) / CO_B));
-  int rc = ck_set_smem(convk_fwd_kernel<K, S>, smem);
+  int rc;
+  if (nbuf == 2) {
+    rc = ck_set_smem(convk_fwd_kernel<K, S, 2>, smem);
+    if (!rc) convk_fwd_kernel<K, S, 2><<<grid, CK_NT, smem, s>>>(op, WC);
+  } else {
+    rc = ck_set_smem(convk_fwd_kernel<K, S, 1>, smem);
+    if (!rc) convk_fwd_kernel<K, S, 1><<<grid, CK_NT, smem, s>>>(op, WC);
+  }
   if (rc) return rc;
-  convk_fwd_kernel<K, S><<<grid, CK_NT, smem, s>>>(op, WC);
   note_launch();
   return check_launch("convk_fwd");
 }
@@ -539,11 +597,23 @@ static int launch_bwdd_k(const SeistOp& op, cudaStream_t s) {
   const int gs_in = op.Cin / op.groups;
   const int WC = pick_wc(gs_in * (8 / CPW)), WP = 8 / WC, CI_B = CPW * WC, TLo = 128 * WP;
   const int width = TLo + KE - 1, pitch = ((width + 3) & ~3) + 4;
-  const size_t smem = sizeof(float) * ((size_t)CK_CIC * pitch + (size_t)CK_CIC * KE * 8 * WC + 8 * 16);
+  const bool has_bn = op.out.bn >= 0 && op.out.g != nullptr;
+  const bool need_x = has_bn || op.out_act == SEIST_OUT_SIGMOID;
+  const int nraw = !need_x ? 1 : ((has_bn && op.out_dxd != nullptr) ? 3 : 2);
+  const size_t z_f = (size_t)CK_CIC * pitch, w_f = (size_t)CK_CIC * KE * 8 * WC;
+  auto bytes = [&](int nbuf) { return sizeof(float) * (8 * 16 + nbuf * (nraw * z_f + w_f)); };
+  const int nbuf = ck_pick_nbuf(bytes(1), bytes(2));
+  const size_t smem = bytes(nbuf);
   dim3 grid(((op.L_in + S - 1) / S + TLo - 1) / TLo, op.N, op.groups * ((gs_in + CI_B - 1) / CI_B));
-  int rc = ck_set_smem(convk_bwd_data_kernel<K, S>, smem);
+  int rc;
+  if (nbuf == 2) {
+    rc = ck_set_smem(convk_bwd_data_kernel<K, S, 2>, smem);
+    if (!rc) convk_bwd_data_kernel<K, S, 2><<<grid, CK_NT, smem, s>>>(op, WC, nraw);
+  } else {
+    rc = ck_set_smem(convk_bwd_data_kernel<K, S, 1>, smem);
+    if (!rc) convk_bwd_data_kernel<K, S, 1><<<grid, CK_NT, smem, s>>>(op, WC, nraw);
+  }
   if (rc) return rc;
-  convk_bwd_data_kernel<K, S><<<grid, CK_NT, smem, s>>>(op, WC);
   note_launch();
   return check_launch("convk_bwd_data");
 }

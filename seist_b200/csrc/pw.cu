@@ -18,6 +18,15 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// per-thread asynchronous copy ring (LDGSTS, helpers in common.cuh): a thread copies ITS OWN 16-byte operands global ->
+// shared several contraction steps ahead and reads them back from the same slot: no registers are held while the loads
+// are in flight and no cross-thread synchronisation is needed (cp.async.wait_group orders the issuing thread's own copies).
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+
 struct PwChan {          // one reduction / target channel, resolved once per CTA
   const float* x;        // row base for n = 0
   float* g;              // gradient row base for n = 0 (backward targets) or nullptr
@@ -306,8 +315,10 @@ struct PwOut {   // per output channel of the forward op, resolved once per CTA
   float A, Bx, Cc;
 };
 
-template <int CI_T, bool F_ELEM, bool F_GELU, bool F_POOL = false>
-__global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G) {
+constexpr int PW_RING_S = 4;                                   // ring stages (PW_RING_S - 1 contraction steps in flight)
+constexpr int PW_RING_STAGE_B = PW_BD_CG * 3 * PW_NT * 16;     // bytes per stage: [channel][dxd | du | x][thread] float4
+template <int CI_T, bool F_ELEM, bool F_GELU, bool F_POOL = false, bool RING = false>
+__global__ void __launch_bounds__(PW_NT, RING ? 3 : 4) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G, const int pre) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cout = op.Cout, Cout4 = (Cout + 3) & ~3, Cin = op.Cin;
   PwChan* ch_s = reinterpret_cast<PwChan*>(sm_raw);                       // [CI_T] targets
@@ -316,6 +327,13 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
   float* red_s = w_s + Cout4 * CI_T;                                      // [4][2*CI_T]
   float* st_s = red_s + 4 * 2 * CI_T;                                     // [4 warps][2*CI_T][32 lanes] running sums
   const int tid = threadIdx.x;
+  // RING: [PW_RING_S] stages behind the statistics (16-byte aligned: every carve-up above is a multiple of 16 bytes)
+  const uint32_t ring = smem_addr(st_s + 4 * 2 * CI_T * 32) + tid * 16;
+  // epilogue operands of the targets (x for khat / GELU' [pre & 1], the old gradient when accumulating [pre & 2]):
+  // copied asynchronously at the start of a quad group, so that their latency hides behind the contraction loop
+  // instead of being exposed once per batch of PW_BD_EB channels.  [plane][CI_T][thread] float4
+  const uint32_t pre_x = ring + (RING ? PW_RING_S * PW_RING_STAGE_B : 0);
+  const uint32_t pre_o = pre_x + ((pre & 1) ? CI_T * PW_NT * 16 : 0);
   const int ci_base = blockIdx.y * CI_T;
   const int L = op.L_out, LQ = L >> 2;
 
@@ -352,6 +370,43 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
 #pragma unroll
   for (int i = 0; i < 2 * CI_T; ++i) my_st[i * 32] = 0.f;
 
+  // RING: issue cursor over the flattened (quad group g, channel step) sequence, PW_RING_S - 1 steps ahead of the
+  // consumer, so the copies of the next quad group are already in flight during the epilogue of the current one
+  int ig = 0, ico = 0, istage = 0, cstage = 0;
+  size_t iobase = 0;
+  auto quad_base = [&](int g) -> size_t {
+    const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
+    const bool ok = f < NQ;
+    const int n = ok ? (int)(f / LQ) : 0;
+    const int l = ok ? (int)(f - (long long)n * LQ) * 4 : 0;
+    return ((size_t)n * op.out.Ct + op.out.c0) * (size_t)L + l;
+  };
+  auto issue_step = [&]() {
+    if (ig < G) {
+      const uint32_t dst0 = ring + istage * PW_RING_STAGE_B;
+#pragma unroll
+      for (int j = 0; j < PW_BD_CG; ++j) {
+        const size_t off = iobase + (size_t)min(ico + j, Cout - 1) * L;
+        const uint32_t dst = dst0 + j * (3 * PW_NT * 16);
+        if (op.out_dxd) cp_async16(dst, op.out_dxd + off);
+        if (has_bn) cp_async16(dst + PW_NT * 16, op.out.g + off);
+        if (need_x) cp_async16(dst + 2 * PW_NT * 16, op.out.x + off);
+      }
+      ico += PW_BD_CG;
+      if (ico >= Cout4) {
+        ico = 0;
+        if (++ig < G) iobase = quad_base(ig);
+      }
+    }
+    cp_async_commit();   // one group per step (possibly empty) keeps the wait count uniform
+    istage = (istage + 1) & (PW_RING_S - 1);
+  };
+  if constexpr (RING) {
+    iobase = quad_base(0);
+#pragma unroll
+    for (int s = 0; s < PW_RING_S - 1; ++s) issue_step();
+  }
+
   for (int g = 0; g < G; ++g) {
     const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
     const bool ok = f < NQ;
@@ -364,15 +419,40 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[c][q] = make_float2(0.f, 0.f);
     const size_t obase = ((size_t)n * op.out.Ct + op.out.c0) * (size_t)L + l;
+    if (!F_POOL && pre && ok) {
+#pragma unroll
+      for (int col = 0; col < CI_T; ++col) {
+        const PwChan& c = ch_s[col];
+        if (c.g == nullptr) continue;
+        const long long off = (long long)n * c.nstride + l;
+        if ((pre & 1) && ((F_GELU && c.act == SEIST_ACT_GELU) || c.bn >= 0)) cp_async16(pre_x + col * (PW_NT * 16), c.x + off);
+        if ((pre & 2) && c.accum) cp_async16(pre_o + col * (PW_NT * 16), c.g + off);
+      }
+      cp_async_commit();
+    }
     for (int co0 = 0; co0 < Cout4; co0 += PW_BD_CG) {
       float4 dx[PW_BD_CG], du[PW_BD_CG], xo[PW_BD_CG];
+      if constexpr (RING) {
+        issue_step();
+        cp_async_wait<PW_RING_S - 1>();
+        const uint32_t src0 = ring + cstage * PW_RING_STAGE_B;
+        cstage = (cstage + 1) & (PW_RING_S - 1);
 #pragma unroll
-      for (int j = 0; j < PW_BD_CG; ++j) {
-        const int co = min(co0 + j, Cout - 1);
-        const size_t off = obase + (size_t)co * L;
-        dx[j] = op.out_dxd ? ldg4(op.out_dxd + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-        du[j] = has_bn ? ldg4(op.out.g + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xo[j] = need_x ? ldg4(op.out.x + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < PW_BD_CG; ++j) {
+          const uint32_t src = src0 + j * (3 * PW_NT * 16);
+          dx[j] = op.out_dxd ? lds4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          du[j] = has_bn ? lds4(src + PW_NT * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xo[j] = need_x ? lds4(src + 2 * PW_NT * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < PW_BD_CG; ++j) {
+          const int co = min(co0 + j, Cout - 1);
+          const size_t off = obase + (size_t)co * L;
+          dx[j] = op.out_dxd ? ldg4(op.out_dxd + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+          du[j] = has_bn ? ldg4(op.out.g + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xo[j] = need_x ? ldg4(op.out.x + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
       for (int j = 0; j < PW_BD_CG; ++j) {
@@ -463,6 +543,7 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
     // targets in batches of PW_BD_EB channels: all loads of a batch (x for khat / GELU', the old gradient when
     // accumulating) are issued before its first store, so their latency overlaps instead of serialising
     // load -> use -> store once per channel (the compiler cannot hoist loads over possibly aliasing stores)
+    if (pre) cp_async_wait<0>();
 #pragma unroll
     for (int cb = 0; cb < CI_T; cb += PW_BD_EB) {
       float4 xv[PW_BD_EB], ov[PW_BD_EB];
@@ -471,8 +552,11 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
         const PwChan& c = ch_s[cb + u];
         const long long off = (long long)n * c.nstride + l;
         const bool live = c.g != nullptr;
-        xv[u] = (live && ((F_GELU && c.act == SEIST_ACT_GELU) || c.bn >= 0)) ? ldg4(c.x + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ov[u] = (live && c.accum) ? ld4(c.g + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool want_x = live && ((F_GELU && c.act == SEIST_ACT_GELU) || c.bn >= 0);
+        if (pre & 1) xv[u] = want_x ? lds4(pre_x + (cb + u) * (PW_NT * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        else xv[u] = want_x ? ldg4(c.x + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pre & 2) ov[u] = (live && c.accum) ? lds4(pre_o + (cb + u) * (PW_NT * 16)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        else ov[u] = (live && c.accum) ? ld4(c.g + off) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < PW_BD_EB; ++u) {
@@ -681,24 +765,39 @@ int launch_pw_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
 }
 
 template <int CIT, bool E, bool Gf>
-static int pw_bwdd_go(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
+static int pw_bwdd_go(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G, int pre) {
+  if (env_knob("SEIST_PW_RING", 0)) {
+    smem += (size_t)PW_RING_S * PW_RING_STAGE_B;
+    int rc = pw_set_smem(pw_bwd_data_kernel<CIT, E, Gf, false, true>, smem);
+    if (!rc) pw_bwd_data_kernel<CIT, E, Gf, false, true><<<grid, PW_NT, smem, s>>>(op, G, 0);
+    return rc;
+  }
+  smem += (size_t)((pre & 1) + ((pre >> 1) & 1)) * CIT * PW_NT * 16;
   int rc = pw_set_smem(pw_bwd_data_kernel<CIT, E, Gf>, smem);
-  if (!rc) pw_bwd_data_kernel<CIT, E, Gf><<<grid, PW_NT, smem, s>>>(op, G);
+  if (!rc) pw_bwd_data_kernel<CIT, E, Gf><<<grid, PW_NT, smem, s>>>(op, G, pre);
   return rc;
 }
 template <int CIT>
 static int pw_bwdd_sel(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
   if (op.pool > 1) {
     int rc = pw_set_smem(pw_bwd_data_kernel<CIT, false, false, true>, smem);
-    if (!rc) pw_bwd_data_kernel<CIT, false, false, true><<<grid, PW_NT, smem, s>>>(op, G);
+    if (!rc) pw_bwd_data_kernel<CIT, false, false, true><<<grid, PW_NT, smem, s>>>(op, G, 0);
     return rc;
   }
+  // epilogue prefetch planes: bit 0 = some target needs x (BatchNorm khat / GELU'), bit 1 = some target accumulates
+  int pre = 0;
+  for (int i = 0; i < op.n_in; ++i) {
+    if (op.in[i].g == nullptr) continue;
+    if (op.in[i].bn >= 0 || op.in[i].act == SEIST_ACT_GELU) pre |= 1;
+    if (op.in[i].accum) pre |= 2;
+  }
+  pre &= env_knob("SEIST_PW_PRE", 0);   // measured: the prefetch planes cost a resident CTA and lose (8.95 -> 9.95 ms per step, gpurun sweep_c): opt-in
   const int sel = (op.p_elem > 0.f ? 2 : 0) | (any_gelu(op) ? 1 : 0);
   switch (sel) {
-    case 0: return pw_bwdd_go<CIT, false, false>(op, s, grid, smem, G);
-    case 1: return pw_bwdd_go<CIT, false, true>(op, s, grid, smem, G);
-    case 2: return pw_bwdd_go<CIT, true, false>(op, s, grid, smem, G);
-    default: return pw_bwdd_go<CIT, true, true>(op, s, grid, smem, G);
+    case 0: return pw_bwdd_go<CIT, false, false>(op, s, grid, smem, G, pre);
+    case 1: return pw_bwdd_go<CIT, false, true>(op, s, grid, smem, G, pre);
+    case 2: return pw_bwdd_go<CIT, true, false>(op, s, grid, smem, G, pre);
+    default: return pw_bwdd_go<CIT, true, true>(op, s, grid, smem, G, pre);
   }
 }
 
@@ -793,7 +892,7 @@ constexpr int BW_NT = 256;
 
 // BW_PC = output samples per chunk (128, or 512 for narrow tiles where the per-chunk barriers/latency dominate)
 template <int CO_B, int R_B, bool K1, int BW_PC>
-__global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ SeistOp op, const int nci_max) {
+__global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ SeistOp op, const int nci_max, const int async_in) {
   constexpr int BW_PITCH = BW_PC + 4;   // input row pitch (floats), keeps 16-byte alignment
   constexpr int BW_GP = 2 * BW_PC + 8;  // gacc channel-PAIR row pitch: g_s[pr][2*s + half] (FFMA2 operand pairs)
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -867,6 +966,25 @@ __global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ S
     const int n = tile / chunks_per_n;
     const int l0 = (tile - n * chunks_per_n) * BW_PC;
     const float pf = path_factor(op, seed, n) * alpha_factor(op, seed, n);
+    // ---- conv-input rows, k = 1 fast path: raw 16-byte asynchronous copies, ALL in flight at once and behind the
+    // gacc loads below; every thread later transforms its own quads in place (no barrier in between).  The former
+    // load -> transform -> store loop exposed one memory latency per quad (ncu: 37 % of the kernel's stall samples
+    // on the first use of that load)
+    const bool in_async = K1 && vec && plain && async_in;
+    if (in_async) {
+      for (int idx = tid; idx < nci * QPR; idx += BW_NT) {
+        const int row = idx / QPR, q = idx - row * QPR;
+        const int l = l0 + 4 * q;
+        float* dst = in_s + row * pitch + 4 * q;
+        if (l < L) {
+          const PwChan& c = ch_s[row];
+          cp_async16(smem_addr(dst), c.x + (long long)n * c.nstride + l);
+        } else {
+          st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+      cp_async_commit();
+    }
     // ---- gacc rows ------------------------------------------------------------------------------
     if (vec) {
       for (int idx = tid; idx < (CO_B / 2) * QPR; idx += BW_NT) {
@@ -945,6 +1063,16 @@ __global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ S
         }
         st4(in_s + row * pitch + 4 * q, v);
       }
+    } else if (in_async) {
+      cp_async_wait<0>();
+      for (int idx = tid; idx < nci * QPR; idx += BW_NT) {
+        const int row = idx / QPR, q = idx - row * QPR;
+        const PwChan& c = ch_s[row];
+        if (l0 + 4 * q < L && (c.act != SEIST_ACT_NONE || c.sc != 1.f || c.sh != 0.f)) {
+          float* dst = in_s + row * pitch + 4 * q;
+          st4(dst, apply_view(ld4(dst), c.sc, c.sh, c.act));
+        }
+      }
     } else if (K1 && vec && plain) {
       for (int idx = tid; idx < nci * QPR; idx += BW_NT) {
         const int row = idx / QPR, q = idx - row * QPR;
@@ -960,28 +1088,15 @@ __global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ S
       if (op.up_src_L > 0) {
         stage_upsampled_rows(op, n, ci_lo, nci, in_s, pitch, width, p_base, src_s, width + 4, Lsrc, ratio);
       } else
-      for (int r = warp; r < nci; r += BW_NT / 32) {
-        const RowSrc rs = make_row(op, n, ci_lo + r);
-        float* dst = in_s + r * pitch;
-        if (plain) {
-          for (int pos0 = lane; pos0 < width; pos0 += 32 * 4) {
-            float v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int p = p_base + pos0 + 32 * u;
-              v[u] = (pos0 + 32 * u < width && p >= 0 && p < op.L_in) ? rs.x[p] : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int pos = pos0 + 32 * u, p = p_base + pos;
-              if (pos < width) {
-                float t = fmaf(rs.sc, v[u], rs.sh);
-                if (rs.act == SEIST_ACT_GELU) t = gelu_f(t);
-                dst[pos] = (p >= 0 && p < op.L_in) ? t : 0.f;
-              }
-            }
-          }
-        } else {
+      if (plain) {
+        rows_issue_plain(op, n, ci_lo, nci, nci, in_s, pitch, width, p_base);
+        cp_async_commit();
+        cp_async_wait<0>();
+        rows_transform_plain(op, n, ci_lo, nci, in_s, pitch, width, p_base);
+      } else {
+        for (int r = warp; r < nci; r += BW_NT / 32) {
+          const RowSrc rs = make_row(op, n, ci_lo + r);
+          float* dst = in_s + r * pitch;
           for (int pos = lane; pos < width; pos += 32) dst[pos] = conv_input_at(op, rs, p_base + pos, Lsrc, ratio);
         }
       }
@@ -1077,7 +1192,7 @@ static int launch_bww_pc(const SeistOp& op, cudaStream_t s, int sm_count) {
   if (gx < 1) gx = 1;
   int rc = pw_set_smem(bww_kernel<CO_B, R_B, K1, BW_PC>, smem);
   if (rc) return rc;
-  bww_kernel<CO_B, R_B, K1, BW_PC><<<dim3((unsigned)gx, gy, gz), BW_NT, smem, s>>>(op, nci_max);
+  bww_kernel<CO_B, R_B, K1, BW_PC><<<dim3((unsigned)gx, gy, gz), BW_NT, smem, s>>>(op, nci_max, env_knob("SEIST_ASYNC", 7) & 1);
   note_launch();
   return check_launch("bww");
 }
