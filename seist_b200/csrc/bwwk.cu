@@ -122,30 +122,12 @@ __global__ void __launch_bounds__(BK_NT, (K <= 9 && NPR == 2) ? 3 : 2) bwwk_kern
             if (has_bn) {
               const float4 du = bk_ldg4(op.out.g + off);
               const BkOut o = oc_s[row];
-              gv.x += fmaf(o.A, du.x, fmaf(o.Bx, x.x, o.Cc));
-              gv.y += fmaf(o.A, du.y, fmaf(o.Bx, x.y, o.Cc));
-              gv.z += fmaf(o.A, du.z, fmaf(o.Bx, x.z, o.Cc));
-              gv.w += fmaf(o.A, du.w, fmaf(o.Bx, x.w, o.Cc));
+              gv = add4(gv, fma4(splat4(o.A), du, fma4(splat4(o.Bx), x, splat4(o.Cc))));
             }
-            if (op.out_act == SEIST_OUT_SIGMOID) {
-              gv.x *= x.x * (1.f - x.x);
-              gv.y *= x.y * (1.f - x.y);
-              gv.z *= x.z * (1.f - x.z);
-              gv.w *= x.w * (1.f - x.w);
-            }
+            if (op.out_act == SEIST_OUT_SIGMOID) gv = mul4(gv, mul4(x, fma4(x, splat4(-1.f), splat4(1.f))));
           }
-          gv.x *= pf;
-          gv.y *= pf;
-          gv.z *= pf;
-          gv.w *= pf;
-          if (op.p_elem > 0.f) {
-            const uint64_t e = ((uint64_t)n * op.Cout + co) * (uint64_t)L + l;
-            const float4 kp = keep4(op.p_elem, seed, op.seed_elem, e);
-            gv.x *= kp.x;
-            gv.y *= kp.y;
-            gv.z *= kp.z;
-            gv.w *= kp.w;
-          }
+          gv = scale4(gv, pf);
+          if (op.p_elem > 0.f) gv = mul4(gv, keep4(op.p_elem, seed, op.seed_elem, ((uint64_t)n * op.Cout + co) * (uint64_t)L + l));
         }
         gh[h] = gv;
       }

@@ -54,6 +54,78 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const float pdf = 0.39894228040143267794f * fast_ex2(-0.72134752044448170368f * x * x);
   return fmaf(x, pdf, cdf);
 }
+// ---- packed (two elements per instruction) versions: FMUL2 / FADD2 / FFMA2 ----------------------------------------------
+// The element-wise prologue / epilogue math (BN affine, GELU, GELU', BN-backward combine) was 40 % of the executed
+// instructions of the narrow 1x1 kernels as scalar FMUL / FFMA / FADD (ncu, profiles/r2_pw_bwd_data_mix.txt) against 11 %
+// for the contraction itself.  The packed forms issue half as many instructions; only |.|, copysign and the two MUFU per
+// element stay scalar.  gelu2 is bit-identical to gelu_f per lane (same operations in the same order, the polynomial
+// negated coefficient by coefficient); gelu_grad2 shares erf's exponential with the density term
+// (exp(-z^2), z = x / sqrt 2, is exp(-x^2 / 2)), one MUFU less than gelu_grad_f and equal to it within 2 ulp.
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+// erf(z) per lane; e = exp(-z^2) is returned as well
+__device__ __forceinline__ float2 erf2(float2 z, float2& e) {
+  const float2 a = make_float2(fabsf(z.x), fabsf(z.y));
+  const float2 d = fma2(dup2(0.3275911f), a, dup2(1.0f));
+  const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
+  float2 np = fma2(dup2(-1.061405429f), t, dup2(1.453152027f));   // -p
+  np = fma2(np, t, dup2(-1.421413741f));
+  np = fma2(np, t, dup2(0.284496736f));
+  np = fma2(np, t, dup2(-0.254829592f));
+  const float2 q = mul2(mul2(dup2(-1.4426950408889634f), a), a);
+  e = make_float2(fast_ex2(q.x), fast_ex2(q.y));
+  const float2 r = fma2(mul2(np, t), e, dup2(1.0f));
+  return make_float2(copysignf(r.x, z.x), copysignf(r.y, z.y));
+}
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  float2 e;
+  const float2 erf = erf2(mul2(x, dup2(0.70710678118654752440f)), e);
+  return mul2(mul2(dup2(0.5f), x), add2(dup2(1.0f), erf));
+}
+__device__ __forceinline__ float2 gelu_grad2(float2 x) {
+  float2 e;
+  const float2 erf = erf2(mul2(x, dup2(0.70710678118654752440f)), e);
+  const float2 cdf = fma2(dup2(0.5f), erf, dup2(0.5f));
+  return fma2(x, mul2(dup2(0.39894228040143267794f), e), cdf);
+}
+__device__ __forceinline__ float4 gelu4(float4 v) {
+  const float2 a = gelu2(make_float2(v.x, v.y)), b = gelu2(make_float2(v.z, v.w));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 gelu_grad4(float4 v) {
+  const float2 a = gelu_grad2(make_float2(v.x, v.y)), b = gelu_grad2(make_float2(v.z, v.w));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+// sc * v + sh per element
+__device__ __forceinline__ float4 affine4(float4 v, float sc, float sh) {
+  const float2 a = fma2(dup2(sc), make_float2(v.x, v.y), dup2(sh)), b = fma2(dup2(sc), make_float2(v.z, v.w), dup2(sh));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) {
+  const float2 lo = mul2(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = mul2(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 scale4(float4 a, float s) { return mul4(a, make_float4(s, s, s, s)); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  const float2 lo = add2(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = add2(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// a * b + c per element
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+  const float2 lo = fma2(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+  const float2 hi = fma2(make_float2(a.z, a.w), make_float2(b.z, b.w), make_float2(c.z, c.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 splat4(float s) { return make_float4(s, s, s, s); }
+// sum of the four elements / dot product of two quads (pairwise: (x + z) + (y + w))
+__device__ __forceinline__ float sum4(float4 a) {
+  const float2 s = add2(make_float2(a.x, a.y), make_float2(a.z, a.w));
+  return s.x + s.y;
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+  const float2 s = fma2(make_float2(a.z, a.w), make_float2(b.z, b.w), mul2(make_float2(a.x, a.y), make_float2(b.x, b.y)));
+  return s.x + s.y;
+}
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 // ---- asynchronous global -> shared copies (LDGSTS) ---------------------------------------------------------------------

@@ -64,6 +64,21 @@ __device__ __forceinline__ RowSrc make_row(const SeistOp& op, int n, int ci) {
 
 
 
+// BN-apply / GELU of a view on the row elements lane, lane + 32, ... inside [lo, hi), in place in shared memory, two
+// elements per packed instruction
+__device__ __forceinline__ void view_inplace(float* d, int lane, int lo, int hi, const RowSrc& rs) {
+  const float2 sc = dup2(rs.sc), sh = dup2(rs.sh);
+  for (int pos = lane; pos < hi; pos += 64) {
+    const int p1 = pos + 32;
+    const bool ok0 = pos >= lo, ok1 = p1 >= lo && p1 < hi;
+    float2 v = make_float2(ok0 ? d[pos] : 0.f, ok1 ? d[p1] : 0.f);
+    v = fma2(sc, v, sh);
+    if (rs.act == SEIST_ACT_GELU) v = gelu2(v);
+    if (ok0) d[pos] = v.x;
+    if (ok1) d[p1] = v.y;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Asynchronous staging of conv-input rows.  dst[r*pitch + pos] <-> conv-input coordinate p_base + pos of channel
 // ci0 + r.  Element ownership (row = warp + k*nwarps, pos = lane + 32*u) is the same in the issue and the transform
@@ -99,13 +114,7 @@ __device__ __forceinline__ void rows_transform_plain(const SeistOp& op, int n, i
     const RowSrc rs = make_row(op, n, ci0 + r);
     if (rs.act == SEIST_ACT_NONE && rs.sc == 1.f && rs.sh == 0.f) continue;
     float* d = dst + r * pitch;
-    if (rs.act == SEIST_ACT_GELU) {
-      for (int pos = lane; pos < pos_hi; pos += 32)
-        if (pos >= pos_lo) d[pos] = gelu_f(fmaf(rs.sc, d[pos], rs.sh));
-    } else {
-      for (int pos = lane; pos < pos_hi; pos += 32)
-        if (pos >= pos_lo) d[pos] = fmaf(rs.sc, d[pos], rs.sh);
-    }
+    view_inplace(d, lane, pos_lo, pos_hi, rs);
   }
 }
 
@@ -141,11 +150,7 @@ __device__ __forceinline__ void src_transform(const SeistOp& op, int n, int ci0,
   for (int r = warp; r < nrows; r += nwarps) {
     const RowSrc rs = make_row(op, n, ci0 + r);
     float* d = src_s + r * spitch;
-    if (rs.act == SEIST_ACT_GELU) {
-      for (int i = lane; i < count; i += 32) d[i] = gelu_f(fmaf(rs.sc, d[i], rs.sh));
-    } else if (rs.sc != 1.f || rs.sh != 0.f) {
-      for (int i = lane; i < count; i += 32) d[i] = fmaf(rs.sc, d[i], rs.sh);
-    }
+    if (rs.act != SEIST_ACT_NONE || rs.sc != 1.f || rs.sh != 0.f) view_inplace(d, lane, 0, count, rs);
   }
 }
 __device__ __forceinline__ void rows_interpolate(const SeistOp& op, int nrows, float* dst, int pitch, int width, int p_base,

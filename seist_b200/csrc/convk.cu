@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_c
       const int co = co_grp + co0 + r;
       const OutGradCoef kc = out_grad_coef(op, co);
       float* d = zb + r * pitch;
-      for (int pos = lane; pos < pos_hi; pos += 32) {
+      for (int pos = lane; pos < pos_hi; pos += 32) {     // (scalar: the packed form measured slower here)
         if (pos < pos_lo) continue;
         float g = d[pos];
         if (need_x) {

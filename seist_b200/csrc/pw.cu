@@ -54,6 +54,9 @@ __device__ __forceinline__ PwChan make_chan(const SeistOp& op, int ci, bool want
   return c;
 }
 
+// (scalar on purpose: the packed FMUL2 / FADD2 forms of this element-wise math measured SLOWER in the latency-bound 1x1
+// kernels - pw_bwd_data 8.95 -> 9.74 ms, pw_fwd 4.61 -> 4.82 ms per step - while they help the staged kernels, where the
+// transform is a separate pass over shared memory; gpurun sweep_d)
 __device__ __forceinline__ float4 apply_view(float4 v, float sc, float sh, int act) {
   v.x = fmaf(sc, v.x, sh);
   v.y = fmaf(sc, v.y, sh);
@@ -65,6 +68,12 @@ __device__ __forceinline__ float4 apply_view(float4 v, float sc, float sh, int a
     v.z = gelu_f(v.z);
     v.w = gelu_f(v.w);
   }
+  return v;
+}
+// packed variant for the staging passes of the weight-gradient kernel
+__device__ __forceinline__ float4 apply_view2(float4 v, float sc, float sh, int act) {
+  v = affine4(v, sc, sh);
+  if (act == SEIST_ACT_GELU) v = gelu4(v);
   return v;
 }
 
@@ -134,7 +143,10 @@ __device__ __noinline__ float4 pw_keep4(float p, uint64_t seed, uint32_t stream,
 
 // compile-time specialisation keeps the bodies small (instruction cache) and the inner loops free of
 // runtime feature tests: F_ELEM element dropout, F_RES residual views, F_GELU some view applies GELU
-template <int COUT_T, bool F_ELEM, bool F_RES, bool F_GELU, bool F_POOL = false>
+constexpr int PWF_CG = 4;                                    // reduction channels per ring stage
+constexpr int PWF_S = 3;                                     // stages (PWF_S - 1 steps in flight)
+constexpr int PWF_STAGE_B = PWF_CG * PW_NT * 16;             // [channel][thread] float4
+template <int COUT_T, bool F_ELEM, bool F_RES, bool F_GELU, bool F_POOL = false, bool RING = false>
 __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant__ SeistOp op, const int G) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cin = op.Cin, Cin8 = (Cin + 7) & ~7;
@@ -144,6 +156,7 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
   float* red_s = ep_s + 5 * COUT_T;                                       // [4][2*COUT_T]
   float* st_s = red_s + 4 * 2 * COUT_T;                                   // [4 warps][2*COUT_T][32 lanes] running sums
   const int tid = threadIdx.x;
+  const uint32_t ring = smem_addr(st_s + 4 * 2 * COUT_T * 32) + tid * 16;  // RING: [PWF_S] stages (16-byte aligned carve-up)
   const int co_base = blockIdx.y * COUT_T;
   const int L = op.L_out, LQ = L >> 2;
 
@@ -186,6 +199,38 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
 #pragma unroll
   for (int i = 0; i < 2 * COUT_T; ++i) my_st[i * 32] = 0.f;
 
+  // RING: the operands of the contraction travel through a per-thread asynchronous copy ring, PWF_S - 1 steps of
+  // PWF_CG channels ahead of their use and across quad groups (see pw_bwd_data_kernel)
+  int ig = 0, ici = 0, istage = 0, cstage = 0, in_n = 0, in_l = 0;
+  auto quad_nl = [&](int g, int& n, int& l) {
+    const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
+    const bool ok = f < NQ;
+    n = ok ? (int)(f / LQ) : 0;
+    l = ok ? (int)(f - (long long)n * LQ) * 4 : 0;
+  };
+  auto issue_step = [&]() {
+    if (ig < G) {
+      const uint32_t dst0 = ring + istage * PWF_STAGE_B;
+#pragma unroll
+      for (int j = 0; j < PWF_CG; ++j) {
+        const PwChan& c = ch_s[ici + j];
+        cp_async16(dst0 + j * (PW_NT * 16), c.x + (long long)in_n * c.nstride + in_l);
+      }
+      ici += PWF_CG;
+      if (ici >= Cin8) {
+        ici = 0;
+        if (++ig < G) quad_nl(ig, in_n, in_l);
+      }
+    }
+    cp_async_commit();
+    istage = istage + 1 == PWF_S ? 0 : istage + 1;
+  };
+  if constexpr (RING) {
+    quad_nl(0, in_n, in_l);
+#pragma unroll
+    for (int s = 0; s < PWF_S - 1; ++s) issue_step();
+  }
+
   for (int g = 0; g < G; ++g) {
     const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
     const bool ok = f < NQ;
@@ -196,6 +241,30 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
     for (int c = 0; c < COUT_T / 2; ++c)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[c][q] = make_float2(0.f, 0.f);
+    if constexpr (RING) {
+      for (int ci0 = 0; ci0 < Cin8; ci0 += PWF_CG) {
+        issue_step();
+        cp_async_wait<PWF_S - 1>();
+        const uint32_t src0 = ring + cstage * PWF_STAGE_B;
+        cstage = cstage + 1 == PWF_S ? 0 : cstage + 1;
+#pragma unroll
+        for (int j = 0; j < PWF_CG; ++j) {
+          const PwChan& c = ch_s[ci0 + j];
+          float4 u = apply_view(lds4(src0 + j * (PW_NT * 16)), c.sc, c.sh, 0);
+          if (F_GELU && c.act == SEIST_ACT_GELU) u = pw_gelu4(u);
+          const float2* wr = reinterpret_cast<const float2*>(w_s + (ci0 + j) * COUT_T);
+          const float2 ux = dup2(u.x), uy = dup2(u.y), uz = dup2(u.z), uw = dup2(u.w);
+#pragma unroll
+          for (int cp = 0; cp < COUT_T / 2; ++cp) {
+            const float2 w = wr[cp];
+            acc[cp][0] = fma2(w, ux, acc[cp][0]);
+            acc[cp][1] = fma2(w, uy, acc[cp][1]);
+            acc[cp][2] = fma2(w, uz, acc[cp][2]);
+            acc[cp][3] = fma2(w, uw, acc[cp][3]);
+          }
+        }
+      }
+    } else
     for (int ci0 = 0; ci0 < Cin8; ci0 += 8) {
       float4 v[8];
 #pragma unroll
@@ -315,10 +384,10 @@ struct PwOut {   // per output channel of the forward op, resolved once per CTA
   float A, Bx, Cc;
 };
 
-constexpr int PW_RING_S = 4;                                   // ring stages (PW_RING_S - 1 contraction steps in flight)
+constexpr int PW_RING_S = 3;                                   // ring stages (PW_RING_S - 1 contraction steps in flight)
 constexpr int PW_RING_STAGE_B = PW_BD_CG * 3 * PW_NT * 16;     // bytes per stage: [channel][dxd | du | x][thread] float4
 template <int CI_T, bool F_ELEM, bool F_GELU, bool F_POOL = false, bool RING = false>
-__global__ void __launch_bounds__(PW_NT, RING ? 3 : 4) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G, const int pre) {
+__global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_constant__ SeistOp op, const int G, const int pre) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cout = op.Cout, Cout4 = (Cout + 3) & ~3, Cin = op.Cin;
   PwChan* ch_s = reinterpret_cast<PwChan*>(sm_raw);                       // [CI_T] targets
@@ -399,7 +468,7 @@ __global__ void __launch_bounds__(PW_NT, RING ? 3 : 4) pw_bwd_data_kernel(const 
       }
     }
     cp_async_commit();   // one group per step (possibly empty) keeps the wait count uniform
-    istage = (istage + 1) & (PW_RING_S - 1);
+    istage = istage + 1 == PW_RING_S ? 0 : istage + 1;
   };
   if constexpr (RING) {
     iobase = quad_base(0);
@@ -436,7 +505,7 @@ __global__ void __launch_bounds__(PW_NT, RING ? 3 : 4) pw_bwd_data_kernel(const 
         issue_step();
         cp_async_wait<PW_RING_S - 1>();
         const uint32_t src0 = ring + cstage * PW_RING_STAGE_B;
-        cstage = (cstage + 1) & (PW_RING_S - 1);
+        cstage = cstage + 1 == PW_RING_S ? 0 : cstage + 1;
 #pragma unroll
         for (int j = 0; j < PW_BD_CG; ++j) {
           const uint32_t src = src0 + j * (3 * PW_NT * 16);
@@ -705,7 +774,8 @@ static int pick_G(long long nq, int tiles_y, int sm_count) {
   // enough CTAs for ~4 waves, but several quads per thread to amortise the per-CTA setup / reduction
   long long ctas = (nq + PW_NT - 1) / PW_NT;
   int G = 1;
-  while (G < 8 && (ctas / (2 * G)) * tiles_y >= 4LL * sm_count) G *= 2;
+  const int gmax = env_knob("SEIST_PW_GMAX", 8);
+  while (G < gmax && (ctas / (2 * G)) * tiles_y >= 4LL * sm_count) G *= 2;
   return G;
 }
 
@@ -726,6 +796,12 @@ static bool any_gelu(const SeistOp& op) {
 
 template <int COT, bool E, bool R, bool Gf>
 static int pw_fwd_go(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
+  if (env_knob("SEIST_PW_RING", 1) & 2) {
+    smem += (size_t)PWF_S * PWF_STAGE_B;
+    int rc = pw_set_smem(pw_fwd_kernel<COT, E, R, Gf, false, true>, smem);
+    if (!rc) pw_fwd_kernel<COT, E, R, Gf, false, true><<<grid, PW_NT, smem, s>>>(op, G);
+    return rc;
+  }
   int rc = pw_set_smem(pw_fwd_kernel<COT, E, R, Gf>, smem);
   if (!rc) pw_fwd_kernel<COT, E, R, Gf><<<grid, PW_NT, smem, s>>>(op, G);
   return rc;
@@ -766,7 +842,7 @@ int launch_pw_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
 
 template <int CIT, bool E, bool Gf>
 static int pw_bwdd_go(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G, int pre) {
-  if (env_knob("SEIST_PW_RING", 0)) {
+  if (env_knob("SEIST_PW_RING", 1) & 1) {
     smem += (size_t)PW_RING_S * PW_RING_STAGE_B;
     int rc = pw_set_smem(pw_bwd_data_kernel<CIT, E, Gf, false, true>, smem);
     if (!rc) pw_bwd_data_kernel<CIT, E, Gf, false, true><<<grid, PW_NT, smem, s>>>(op, G, 0);
@@ -1003,30 +1079,12 @@ __global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ S
               if (has_bn) {
                 const float4 du = ldg4(op.out.g + off);
                 const PwOut o = oc_s[row];
-                gv.x += fmaf(o.A, du.x, fmaf(o.Bx, x.x, o.Cc));
-                gv.y += fmaf(o.A, du.y, fmaf(o.Bx, x.y, o.Cc));
-                gv.z += fmaf(o.A, du.z, fmaf(o.Bx, x.z, o.Cc));
-                gv.w += fmaf(o.A, du.w, fmaf(o.Bx, x.w, o.Cc));
+                gv = add4(gv, fma4(splat4(o.A), du, fma4(splat4(o.Bx), x, splat4(o.Cc))));
               }
-              if (op.out_act == SEIST_OUT_SIGMOID) {
-                gv.x *= x.x * (1.f - x.x);
-                gv.y *= x.y * (1.f - x.y);
-                gv.z *= x.z * (1.f - x.z);
-                gv.w *= x.w * (1.f - x.w);
-              }
+              if (op.out_act == SEIST_OUT_SIGMOID) gv = mul4(gv, mul4(x, fma4(x, splat4(-1.f), splat4(1.f))));
             }
-            gv.x *= pf;
-            gv.y *= pf;
-            gv.z *= pf;
-            gv.w *= pf;
-            if (op.p_elem > 0.f) {
-              const uint64_t e = ((uint64_t)n * Cout + co) * (uint64_t)L + l;
-              const float4 kp = keep4(op.p_elem, seed, op.seed_elem, e);
-              gv.x *= kp.x;
-              gv.y *= kp.y;
-              gv.z *= kp.z;
-              gv.w *= kp.w;
-            }
+            gv = scale4(gv, pf);
+            if (op.p_elem > 0.f) gv = mul4(gv, keep4(op.p_elem, seed, op.seed_elem, ((uint64_t)n * Cout + co) * (uint64_t)L + l));
           }
           gh[h] = gv;
         }
@@ -1070,7 +1128,7 @@ __global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ S
         const PwChan& c = ch_s[row];
         if (l0 + 4 * q < L && (c.act != SEIST_ACT_NONE || c.sc != 1.f || c.sh != 0.f)) {
           float* dst = in_s + row * pitch + 4 * q;
-          st4(dst, apply_view(ld4(dst), c.sc, c.sh, c.act));
+          st4(dst, apply_view2(ld4(dst), c.sc, c.sh, c.act));
         }
       }
     } else if (K1 && vec && plain) {
