@@ -405,6 +405,13 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_c
       const bool inside = pq < op.L_in;
       const int m2 = pq >> 1;                               // source index 2m
       const bool first = pq == 0, last = pq + 4 >= op.L_in;
+      // the source samples of all 8 channels first: one exposed memory latency instead of one per channel
+      float2 x2v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int ci = ci_base + wc * 8 + c;
+        x2v[c] = (inside && ci < ci_end) ? *reinterpret_cast<const float2*>(view_row(v, n, ci) + m2) : make_float2(0.f, 0.f);
+      }
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const int ci = ci_base + wc * 8 + c;
@@ -430,7 +437,7 @@ __global__ void __launch_bounds__(CK_NT, 3) convk_bwd_data_kernel(const __grid_c
         if (v.bn >= 0) view_khat(op, v, ci, mu, istd);
         const float* xr = view_row(v, n, ci);
         float* gr = view_grad_row(v, n, ci);
-        const float2 x2 = *reinterpret_cast<const float2*>(xr + m2);
+        const float2 x2 = x2v[c];
         if (v.act == SEIST_ACT_GELU) {
           gb *= gelu_grad_f(fmaf(sc, x2.x, sh));
           gc *= gelu_grad_f(fmaf(sc, x2.y, sh));

@@ -27,6 +27,13 @@ __device__ __forceinline__ float4 lds4(uint32_t a) {
   return v;
 }
 
+// quad group g of this CTA.  G > 0: the CTA owns G consecutive groups (grid = groups / G).  G < 0: "persistent" launch, the
+// grid is exactly the number of CTAs resident at once and a CTA walks the groups blockIdx.x, blockIdx.x + gridDim.x, ...
+// (-G of them): no partially filled last wave, and the CTAs running together touch one contiguous region
+__device__ __forceinline__ long long pw_group(int g, int G) {
+  return G > 0 ? (long long)blockIdx.x * G + g : (long long)blockIdx.x + (long long)g * gridDim.x;
+}
+
 struct PwChan {          // one reduction / target channel, resolved once per CTA
   const float* x;        // row base for n = 0
   float* g;              // gradient row base for n = 0 (backward targets) or nullptr
@@ -192,6 +199,7 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
 
   const uint64_t seed = load_seed(op.step_seed);
   const long long NQ = (long long)op.N * LQ;
+  const int Gn = G < 0 ? -G : G;
   const bool stats = (op.out.bn >= 0) && op.bn_table[op.out.bn >= 0 ? op.out.bn : 0].use_batch;
   // BatchNorm sums of the result live in shared memory (one private slot per thread and statistic) between
   // quads: in registers they would cost 2*COUT_T registers across the whole contraction loop
@@ -203,13 +211,13 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
   // PWF_CG channels ahead of their use and across quad groups (see pw_bwd_data_kernel)
   int ig = 0, ici = 0, istage = 0, cstage = 0, in_n = 0, in_l = 0;
   auto quad_nl = [&](int g, int& n, int& l) {
-    const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
+    const long long f = pw_group(g, G) * PW_NT + tid;
     const bool ok = f < NQ;
     n = ok ? (int)(f / LQ) : 0;
     l = ok ? (int)(f - (long long)n * LQ) * 4 : 0;
   };
   auto issue_step = [&]() {
-    if (ig < G) {
+    if (ig < Gn) {
       const uint32_t dst0 = ring + istage * PWF_STAGE_B;
 #pragma unroll
       for (int j = 0; j < PWF_CG; ++j) {
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
       ici += PWF_CG;
       if (ici >= Cin8) {
         ici = 0;
-        if (++ig < G) quad_nl(ig, in_n, in_l);
+        if (++ig < Gn) quad_nl(ig, in_n, in_l);
       }
     }
     cp_async_commit();
@@ -231,8 +239,8 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_fwd_kernel(const __grid_constant_
     for (int s = 0; s < PWF_S - 1; ++s) issue_step();
   }
 
-  for (int g = 0; g < G; ++g) {
-    const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
+  for (int g = 0; g < Gn; ++g) {
+    const long long f = pw_group(g, G) * PW_NT + tid;
     const bool ok = f < NQ;
     const int n = ok ? (int)(f / LQ) : 0;
     const int l = ok ? (int)(f - (long long)n * LQ) * 4 : 0;
@@ -431,6 +439,7 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
 
   const uint64_t seed = load_seed(op.step_seed);
   const long long NQ = (long long)op.N * LQ;
+  const int Gn = G < 0 ? -G : G;
   const bool has_bn = (op.out.bn >= 0 && op.out.g != nullptr);
   const bool need_x = has_bn || op.out_act == SEIST_OUT_SIGMOID;
   // BN-backward sums of the targets live in shared memory (one private slot per thread and statistic)
@@ -444,14 +453,14 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
   int ig = 0, ico = 0, istage = 0, cstage = 0;
   size_t iobase = 0;
   auto quad_base = [&](int g) -> size_t {
-    const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
+    const long long f = pw_group(g, G) * PW_NT + tid;
     const bool ok = f < NQ;
     const int n = ok ? (int)(f / LQ) : 0;
     const int l = ok ? (int)(f - (long long)n * LQ) * 4 : 0;
     return ((size_t)n * op.out.Ct + op.out.c0) * (size_t)L + l;
   };
   auto issue_step = [&]() {
-    if (ig < G) {
+    if (ig < Gn) {
       const uint32_t dst0 = ring + istage * PW_RING_STAGE_B;
 #pragma unroll
       for (int j = 0; j < PW_BD_CG; ++j) {
@@ -464,7 +473,7 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
       ico += PW_BD_CG;
       if (ico >= Cout4) {
         ico = 0;
-        if (++ig < G) iobase = quad_base(ig);
+        if (++ig < Gn) iobase = quad_base(ig);
       }
     }
     cp_async_commit();   // one group per step (possibly empty) keeps the wait count uniform
@@ -476,8 +485,8 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
     for (int s = 0; s < PW_RING_S - 1; ++s) issue_step();
   }
 
-  for (int g = 0; g < G; ++g) {
-    const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
+  for (int g = 0; g < Gn; ++g) {
+    const long long f = pw_group(g, G) * PW_NT + tid;
     const bool ok = f < NQ;
     const int n = ok ? (int)(f / LQ) : 0;
     const int l = ok ? (int)(f - (long long)n * LQ) * 4 : 0;
@@ -678,6 +687,7 @@ __global__ void __launch_bounds__(PW_NT) res_bwd4_kernel(const __grid_constant__
   const int co = blockIdx.y;
   const int L = op.L_out, LQ = L >> 2;
   const long long NQ = (long long)op.N * LQ;
+  const int Gn = G < 0 ? -G : G;
   const uint64_t seed = load_seed(op.step_seed);
   const OutGradCoef kc = out_grad_coef(op, co);
   const bool has_bn = (op.out.bn >= 0 && op.out.g != nullptr);
@@ -689,8 +699,8 @@ __global__ void __launch_bounds__(PW_NT) res_bwd4_kernel(const __grid_constant__
   if (wa && va.bn >= 0) view_khat(op, va, co, amu, aistd);
   if (wb && vb.bn >= 0) view_khat(op, vb, co, bmu, bistd);
   float st[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int g = 0; g < G; ++g) {
-    const long long f = ((long long)blockIdx.x * G + g) * PW_NT + tid;
+  for (int g = 0; g < Gn; ++g) {
+    const long long f = pw_group(g, G) * PW_NT + tid;
     if (f >= NQ) break;
     const int n = (int)(f / LQ);
     const int l = (int)(f - (long long)n * LQ) * 4;
@@ -788,6 +798,27 @@ static int pw_set_smem(K kernel, size_t bytes) {
   return 0;
 }
 
+// persistent sizing of the streaming kernels (see pw_group): exactly the CTAs resident at once, each walking
+// ceil(groups / grid) quad groups.  The former "G consecutive groups per CTA" grids ended in a partially filled
+// wave (typically 1.7 - 2.6 waves).  SEIST_PW_PERSIST=1 enables it (A/B runs; it did not pay, see below).
+static thread_local int tl_sm_count = 0;
+static thread_local long long tl_groups = 0;
+template <typename K>
+static void pw_persist(K kernel, size_t smem, dim3& grid, int& G) {
+  if (!env_knob("SEIST_PW_PERSIST", 0) || tl_sm_count <= 0) return;   // measured: pw_fwd 4.55 -> 4.47 but pw_bwd_data 8.35 -> 8.77 ms per step (gpurun sweep_h): opt-in
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, PW_NT, smem) != cudaSuccess || nb < 1) return;
+  long long gx = (long long)nb * tl_sm_count / grid.y;
+  if (gx < 1) gx = 1;
+  if (gx >= tl_groups) {
+    grid.x = (unsigned)tl_groups;
+    G = 1;
+    return;
+  }
+  grid.x = (unsigned)gx;
+  G = -(int)((tl_groups + gx - 1) / gx);
+}
+
 static bool any_gelu(const SeistOp& op) {
   for (int i = 0; i < op.n_in; ++i)
     if (op.in[i].act == SEIST_ACT_GELU) return true;
@@ -799,10 +830,12 @@ static int pw_fwd_go(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, 
   if (env_knob("SEIST_PW_RING", 1) & 2) {
     smem += (size_t)PWF_S * PWF_STAGE_B;
     int rc = pw_set_smem(pw_fwd_kernel<COT, E, R, Gf, false, true>, smem);
+    pw_persist(pw_fwd_kernel<COT, E, R, Gf, false, true>, smem, grid, G);
     if (!rc) pw_fwd_kernel<COT, E, R, Gf, false, true><<<grid, PW_NT, smem, s>>>(op, G);
     return rc;
   }
   int rc = pw_set_smem(pw_fwd_kernel<COT, E, R, Gf>, smem);
+    pw_persist(pw_fwd_kernel<COT, E, R, Gf>, smem, grid, G);
   if (!rc) pw_fwd_kernel<COT, E, R, Gf><<<grid, PW_NT, smem, s>>>(op, G);
   return rc;
 }
@@ -810,6 +843,7 @@ template <int COT>
 static int pw_fwd_sel(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
   if (op.pool > 1) {
     int rc = pw_set_smem(pw_fwd_kernel<COT, false, false, false, true>, smem);
+    pw_persist(pw_fwd_kernel<COT, false, false, false, true>, smem, grid, G);
     if (!rc) pw_fwd_kernel<COT, false, false, false, true><<<grid, PW_NT, smem, s>>>(op, G);
     return rc;
   }
@@ -834,6 +868,8 @@ int launch_pw_fwd(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int ty = (op.Cout + cot - 1) / cot;
   const int G = pick_G(nq, ty, sm_count);
   dim3 grid((unsigned)((nq + (long long)PW_NT * G - 1) / ((long long)PW_NT * G)), ty);
+  tl_sm_count = sm_count;
+  tl_groups = (nq + PW_NT - 1) / PW_NT;
   const int rc = cot == 16 ? pw_fwd_sel<16>(op, s, grid, smem, G) : pw_fwd_sel<8>(op, s, grid, smem, G);
   if (rc) return rc;
   note_launch();
@@ -845,11 +881,13 @@ static int pw_bwdd_go(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem,
   if (env_knob("SEIST_PW_RING", 1) & 1) {
     smem += (size_t)PW_RING_S * PW_RING_STAGE_B;
     int rc = pw_set_smem(pw_bwd_data_kernel<CIT, E, Gf, false, true>, smem);
+    pw_persist(pw_bwd_data_kernel<CIT, E, Gf, false, true>, smem, grid, G);
     if (!rc) pw_bwd_data_kernel<CIT, E, Gf, false, true><<<grid, PW_NT, smem, s>>>(op, G, 0);
     return rc;
   }
   smem += (size_t)((pre & 1) + ((pre >> 1) & 1)) * CIT * PW_NT * 16;
   int rc = pw_set_smem(pw_bwd_data_kernel<CIT, E, Gf>, smem);
+    pw_persist(pw_bwd_data_kernel<CIT, E, Gf>, smem, grid, G);
   if (!rc) pw_bwd_data_kernel<CIT, E, Gf><<<grid, PW_NT, smem, s>>>(op, G, pre);
   return rc;
 }
@@ -857,6 +895,7 @@ template <int CIT>
 static int pw_bwdd_sel(const SeistOp& op, cudaStream_t s, dim3 grid, size_t smem, int G) {
   if (op.pool > 1) {
     int rc = pw_set_smem(pw_bwd_data_kernel<CIT, false, false, true>, smem);
+    pw_persist(pw_bwd_data_kernel<CIT, false, false, true>, smem, grid, G);
     if (!rc) pw_bwd_data_kernel<CIT, false, false, true><<<grid, PW_NT, smem, s>>>(op, G, 0);
     return rc;
   }
@@ -885,6 +924,8 @@ int launch_pw_bwd_data(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int ty = (op.Cin + cit - 1) / cit;
   const int G = pick_G(nq, ty, sm_count);
   dim3 grid((unsigned)((nq + (long long)PW_NT * G - 1) / ((long long)PW_NT * G)), ty);
+  tl_sm_count = sm_count;
+  tl_groups = (nq + PW_NT - 1) / PW_NT;
   const int rc = cit == 16 ? pw_bwdd_sel<16>(op, s, grid, smem, G) : pw_bwdd_sel<8>(op, s, grid, smem, G);
   if (rc) return rc;
   note_launch();
