@@ -121,13 +121,16 @@ static bool use_tcc(const SeistOp& op, int mode) {
   if (m == 0 || !tcconv_eligible(op, mode)) return false;
   return m == 1 || tcc_auto(op, mode);
 }
-// weight gradient of wide 1x1 convolutions on tcgen05 (bww_tc.cu): wins from 64 reduction channels up (L <= 256 there)
+// weight gradient of wide 1x1 convolutions on tcgen05 (bww_tc.cu).  Timed alone it wins from 64 reduction channels up
+// (37 ops of seist_m_dpk: 2.42 ms against 2.9 ms for the SIMT kernel), but the weight gradients run on the side lane
+// CONCURRENTLY with the data-gradient chain, and there its 148 x 2 CTAs with their large shared-memory / TMEM footprint
+// displace more main-lane CTAs than they save: whole step 36.81 ms with it, 36.44 ms without (gpurun sweep_i, sweep_j).
+// What counts for a side-lane kernel is the step, so it is opt-in: SEIST_BWW_TC=1 (rule below), SEIST_TC=1 (every op).
 static bool use_bww_tc(const SeistOp& op) {
   if (!bww_tc_eligible(op)) return false;
   const int m = tc_mode();
   if (m == 1) return true;
-  const char* e = std::getenv("SEIST_BWW_TC");
-  if (e && e[0] == '0') return false;
+  if (!env_knob("SEIST_BWW_TC", 0)) return false;
   return op.Cin >= 64 && op.Cout >= 32 && op.L_out <= 256;
 }
 

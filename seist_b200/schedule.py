@@ -12,6 +12,7 @@ critical path; what `seist_plan_run2` did before).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Set, Tuple
 
 from . import _lib
@@ -192,9 +193,18 @@ def schedule_lanes(plan, ops, c_ops, n_main: int = 2, cost=_cost) -> dict:
     rec: Dict[int, int] = {}
     n_ev = 0
     cross = 0
+    # the weight gradients behind the last data-gradient op (the first stem block: its input needs no gradient) are the
+    # tail of the step: nothing else is left to overlap with, so they are spread over all lanes instead of queueing on one
+    main_kinds = (L.CONV_BWD_DATA, L.RES_BWD, L.ATT_BWD_Q, L.ATT_BWD_KV, L.HEADVEC_BWD, L.CONV_FWD, L.ATT_FWD, L.HEADVEC_FWD)
+    last_main = max((i for i, op in enumerate(ops) if op.kind in main_kinds), default=len(ops))
+    spread_tail = os.environ.get("SEIST_TAIL_SPREAD", "1") != "0"
+    rr = 0
     for i, op in enumerate(ops):
         d = deps[i]
-        if op.kind in (L.CONV_BWD_W, L.STEM_COMPOSE_BWD):
+        if op.kind == L.CONV_BWD_W and spread_tail and i > last_main:
+            lane = (w_lane + rr) % (n_main + 1)
+            rr += 1
+        elif op.kind in (L.CONV_BWD_W, L.STEM_COMPOSE_BWD):
             lane = w_lane
         else:
             mains = [l for l in range(n_main) if tail[l] in d]
