@@ -173,6 +173,74 @@ __device__ __forceinline__ void rows_interpolate(const SeistOp& op, int nrows, f
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Asynchronous staging of the output-gradient ("gacc") rows of the weight-gradient kernels.
+// g_s holds channel-PAIR rows: the 8 floats at g_s[pr*gpitch + 8*q] are {g[2pr][4q..4q+3] interleaved with
+// g[2pr+1][4q..4q+3]}.  The raw operands of (pr, q) land in exactly those 32 bytes (row 2pr first, then row 2pr+1) and, as
+// far as the op needs them, at the same offset of the planes x_s / d_s; the owning thread (idx -> (pr, q), the same
+// mapping in both functions) later combines them in place: BN backward, sigmoid', drop factors, pair interleave.
+//   plane 0 (g_s): du when the output carries a BatchNorm gradient, else dxd (zeros if absent)
+//   x_s: the forward output (BN backward / sigmoid');  d_s: dxd next to a BatchNorm gradient
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void gacc_issue(const SeistOp& op, int n, int l0, int L, int co_base, int co_hi, int CO_B, int QPR,
+                                           int gpitch, float* g_s, float* x_s, float* d_s, bool has_bn, bool need_x) {
+  const float* src0 = has_bn ? op.out.g : op.out_dxd;
+  const float* src2 = has_bn ? op.out_dxd : nullptr;
+  for (int idx = threadIdx.x; idx < (CO_B / 2) * QPR; idx += NT) {
+    const int pr = idx / QPR, q = idx - pr * QPR;
+    const int l = l0 + 4 * q;
+    const int o8 = pr * gpitch + 8 * q;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int co = co_base + 2 * pr + h;
+      float* d = g_s + o8 + 4 * h;
+      if (co < co_hi && l < L) {
+        const size_t off = ((size_t)n * op.out.Ct + op.out.c0 + co) * (size_t)L + l;
+        if (src0) cp_async16(smem_addr(d), src0 + off);
+        else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (need_x) cp_async16(smem_addr(x_s + o8 + 4 * h), op.out.x + off);
+        if (src2) cp_async16(smem_addr(d_s + o8 + 4 * h), src2 + off);
+      } else {
+        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+}
+template <int NT, typename OC>
+__device__ __forceinline__ void gacc_combine(const SeistOp& op, int n, int l0, int L, int co_base, int co_hi, int CO_B, int QPR,
+                                             int gpitch, float* g_s, const float* x_s, const float* d_s, const OC* oc_s,
+                                             bool has_bn, bool need_x, float pf, uint64_t seed, int Cout_all) {
+  const bool has_d = has_bn && op.out_dxd != nullptr;
+  for (int idx = threadIdx.x; idx < (CO_B / 2) * QPR; idx += NT) {
+    const int pr = idx / QPR, q = idx - pr * QPR;
+    const int l = l0 + 4 * q;
+    const int o8 = pr * gpitch + 8 * q;
+    float4 gh[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = 2 * pr + h, co = co_base + row;
+      float4 gv = *reinterpret_cast<const float4*>(g_s + o8 + 4 * h);
+      if (co < co_hi && l < L) {
+        if (need_x) {
+          const float4 x = *reinterpret_cast<const float4*>(x_s + o8 + 4 * h);
+          if (has_bn) {
+            const OC o = oc_s[row];
+            gv = fma4(splat4(o.A), gv, fma4(splat4(o.Bx), x, splat4(o.Cc)));
+            if (has_d) gv = add4(gv, *reinterpret_cast<const float4*>(d_s + o8 + 4 * h));
+          }
+          if (op.out_act == SEIST_OUT_SIGMOID) gv = mul4(gv, mul4(x, fma4(x, splat4(-1.f), splat4(1.f))));
+        }
+        gv = scale4(gv, pf);
+        if (op.p_elem > 0.f) gv = mul4(gv, keep4(op.p_elem, seed, op.seed_elem, ((uint64_t)n * Cout_all + co) * (uint64_t)L + l));
+      }
+      gh[h] = gv;
+    }
+    *reinterpret_cast<float4*>(g_s + o8) = make_float4(gh[0].x, gh[1].x, gh[0].y, gh[1].y);
+    *reinterpret_cast<float4*>(g_s + o8 + 4) = make_float4(gh[0].z, gh[1].z, gh[0].w, gh[1].w);
+  }
+}
+
 // Two-phase staging of linearly up-sampled rows (reference F.interpolate(mode="linear"), models/seist.py:566):
 // phase 1 brings the SOURCE samples in (asynchronous copies, all in flight at once) and evaluates BN/GELU once per
 // source sample in place, phase 2 interpolates from shared memory, so the activation is not re-evaluated for both

@@ -1009,7 +1009,7 @@ constexpr int BW_NT = 256;
 
 // BW_PC = output samples per chunk (128, or 512 for narrow tiles where the per-chunk barriers/latency dominate)
 template <int CO_B, int R_B, bool K1, int BW_PC>
-__global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ SeistOp op, const int nci_max, const int async_in) {
+__global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ SeistOp op, const int nci_max, const int async_in, const int gx_off) {
   constexpr int BW_PITCH = BW_PC + 4;   // input row pitch (floats), keeps 16-byte alignment
   constexpr int BW_GP = 2 * BW_PC + 8;  // gacc channel-PAIR row pitch: g_s[pr][2*s + half] (FFMA2 operand pairs)
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -1031,6 +1031,8 @@ __global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ S
   PwOut* oc_s = reinterpret_cast<PwOut*>(g_s + ((area_f + 3) & ~3));   // [CO_B]
   PwChan* ch_s = reinterpret_cast<PwChan*>(oc_s + CO_B);                // [nci_max] (k = 1 fast path)
   float* src_s = reinterpret_cast<float*>(ch_s + nci_max + 1);          // [nci_max][width+4] (up-sampled input only)
+  float* gx_s = reinterpret_cast<float*>(sm_raw) + gx_off;              // [2][CO_B/2][BW_GP] raw x / dxd planes (async_in & 2)
+  float* gd_s = gx_s + (CO_B / 2) * BW_GP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int co_base = grp * gs_out + (blockIdx.y - grp * tpg) * CO_B, r_base = blockIdx.z * R_B;
   const int ci_lo = grp * gs_in + r_base / k;
@@ -1103,7 +1105,13 @@ __global__ void __launch_bounds__(BW_NT, 3) bww_kernel(const __grid_constant__ S
       cp_async_commit();
     }
     // ---- gacc rows ------------------------------------------------------------------------------
-    if (vec) {
+    const bool g_async = vec && (async_in & 2);
+    if (g_async) {
+      gacc_issue<BW_NT>(op, n, l0, L, co_base, Cout, CO_B, QPR, BW_GP, g_s, gx_s, gd_s, has_bn, need_x);
+      cp_async_commit();
+      cp_async_wait<0>();
+      gacc_combine<BW_NT>(op, n, l0, L, co_base, Cout, CO_B, QPR, BW_GP, g_s, gx_s, gd_s, oc_s, has_bn, need_x, pf, seed, op.Cout);
+    } else if (vec) {
       for (int idx = tid; idx < (CO_B / 2) * QPR; idx += BW_NT) {
         const int pr = idx / QPR, q = idx - pr * QPR;
         const int l = l0 + 4 * q;
@@ -1281,8 +1289,21 @@ static int launch_bww_pc(const SeistOp& op, cudaStream_t s, int sm_count) {
   const int pitch = K1 ? BW_PITCH : (width | 1);
   int stage_f = (CO_B / 2) * (2 * BW_PC + 8) + nci_max * pitch;
   if (stage_f < BW_NT * 36) stage_f = BW_NT * 36;
-  const size_t smem = sizeof(float) * (size_t)((stage_f + 3) & ~3) + sizeof(PwOut) * CO_B + sizeof(PwChan) * (nci_max + 1) + 64 +
-                      (op.up_src_L > 0 ? sizeof(float) * (size_t)nci_max * (width + 4) : 0);
+  size_t smem = sizeof(float) * (size_t)((stage_f + 3) & ~3) + sizeof(PwOut) * CO_B + sizeof(PwChan) * (nci_max + 1) + 64 +
+                (op.up_src_L > 0 ? sizeof(float) * (size_t)nci_max * (width + 4) : 0);
+  // raw planes of the asynchronous gacc staging (x, dxd next to du) - unless they would cost the second resident CTA
+  int async = env_knob("SEIST_ASYNC", 7);
+  smem = (smem + 15) & ~(size_t)15;
+  const int gx_off = (int)(smem / sizeof(float));
+  {
+    const bool has_bn = op.out.bn >= 0 && op.out.g != nullptr;
+    const bool need_x = has_bn || op.out_act == SEIST_OUT_SIGMOID;
+    const int planes = (need_x ? 1 : 0) + ((has_bn && op.out_dxd != nullptr) ? 1 : 0);
+    const size_t extra = sizeof(float) * (size_t)planes * (CO_B / 2) * (2 * BW_PC + 8);
+    const bool vec = (op.L_out & 3) == 0;
+    if (!vec || (smem <= 113 * 1024 && smem + extra > 113 * 1024)) async &= ~2;
+    if (async & 2) smem += extra;
+  }
   const int R = (op.Cin / op.groups) * k;
   const int gy = op.groups * ((op.Cout / op.groups + CO_B - 1) / CO_B), gz = (R + R_B - 1) / R_B;
   const long tiles = (long)op.N * ((op.L_out + BW_PC - 1) / BW_PC);
@@ -1291,7 +1312,7 @@ static int launch_bww_pc(const SeistOp& op, cudaStream_t s, int sm_count) {
   if (gx < 1) gx = 1;
   int rc = pw_set_smem(bww_kernel<CO_B, R_B, K1, BW_PC>, smem);
   if (rc) return rc;
-  bww_kernel<CO_B, R_B, K1, BW_PC><<<dim3((unsigned)gx, gy, gz), BW_NT, smem, s>>>(op, nci_max, env_knob("SEIST_ASYNC", 7) & 1);
+  bww_kernel<CO_B, R_B, K1, BW_PC><<<dim3((unsigned)gx, gy, gz), BW_NT, smem, s>>>(op, nci_max, async & 3, gx_off);
   note_launch();
   return check_launch("bww");
 }
