@@ -159,13 +159,15 @@ class Engine:
 
     def _lane_streams(self, device):
         """[current stream, aux lane (independent branches), weight-gradient lane] as a ctypes array of stream handles."""
+        from .schedule import n_main_lanes
+        nm = n_main_lanes()
         aux = self._aux.get(device)
-        if aux is None:
-            aux = self._aux[device] = torch.cuda.Stream(device=device, priority=-1)
+        if aux is None or len(aux) != nm - 1:
+            aux = self._aux[device] = [torch.cuda.Stream(device=device, priority=-1) for _ in range(nm - 1)]
         side = self._side.get(device)
         if side is None:
             side = self._side[device] = torch.cuda.Stream(device=device)
-        arr = (ctypes.c_void_p * 3)(_stream_ptr(), aux.cuda_stream, side.cuda_stream)
+        arr = (ctypes.c_void_p * (nm + 1))(_stream_ptr(), *[a.cuda_stream for a in aux], side.cuda_stream)
         return arr
 
     def _run_segments(self, plan: P.Plan, c_ops, segs, stat: torch.Tensor, side: bool = False):
@@ -179,7 +181,7 @@ class Engine:
             # them in the same order, which only stream order guarantees.
             streams = self._lane_streams(plan.device)
             n = segs[0][1] - segs[0][0]
-            _lib.check(lib.seist_plan_run_lanes(base + segs[0][0] * size, n, streams, 3), "seist_plan_run_lanes")
+            _lib.check(lib.seist_plan_run_lanes(base + segs[0][0] * size, n, streams, len(streams)), "seist_plan_run_lanes")
             return
         side_ptr = self._side_stream(plan.device) if side else 0
         for start, end, sync in segs:

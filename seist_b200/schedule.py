@@ -181,9 +181,16 @@ def _cost(op) -> float:
     return float(n) * max(1, f.k) ** 0.5 + 2000.0
 
 
-def schedule_lanes(plan, ops, c_ops, n_main: int = 2, cost=_cost) -> dict:
+def n_main_lanes() -> int:
+    """main lanes (critical chain + independent branches); SEIST_NMAIN=1..3, default 2 (measured: profiles/r2_knob_sweeps.txt)"""
+    return min(3, max(1, int(os.environ.get("SEIST_NMAIN", "2"))))
+
+
+def schedule_lanes(plan, ops, c_ops, n_main: Optional[int] = None, cost=_cost) -> dict:
     """Fill `lane`, `n_wait`, `wait_ev`, `rec_event` of the ctypes descriptors `c_ops`.  Returns a small summary."""
     L = _lib
+    if n_main is None:
+        n_main = n_main_lanes()
     deps = _deps(plan, ops)
     w_lane = n_main                                     # weight-gradient lane
     lane_of: List[int] = []
