@@ -110,6 +110,72 @@ __device__ __forceinline__ float4 pw_load_pooled(const float* src, int P, float 
   return r;
 }
 
+// Backward of AvgPool1d(P) + MaxPool1d(P) in front of a 1x1 conv (reference models/seist.py:62-76) for one target channel
+// of one thread: NJ pooled gradients gq[0..NJ) go to their NJ*P contiguous source samples as g * (1/P + [first arg max of the
+// BN-applied values]).  The source samples are read and written with 16-byte accesses and the arg max is found in
+// registers; the former version walked them with P scalar loads + P/2 float2 loads and stores per pooled sample (5x the
+// time of a plain target of the same size, profiles/r2_op_times_final.json).  s1 / s2: BN-backward sums of the targets.
+template <int P, int NJ>
+__device__ __forceinline__ void pool_route_part(const PwChan& c, const float4* xs, float4* gs, const float* gq, float& s1,
+                                                float& s2) {
+  constexpr int NC = NJ * P / 4;                 // float4 chunks
+  constexpr float invp = 1.f / (float)P;
+  float v[NJ * P];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const float4 q = __ldg(xs + k);
+    v[4 * k] = q.x;
+    v[4 * k + 1] = q.y;
+    v[4 * k + 2] = q.z;
+    v[4 * k + 3] = q.w;
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    int am = 0;
+    float mx = fmaf(c.sc, v[j * P], c.sh);
+#pragma unroll
+    for (int i = 1; i < P; ++i) {
+      const float u = fmaf(c.sc, v[j * P + i], c.sh);
+      if (u > mx) {
+        mx = u;
+        am = i;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const float x = v[j * P + i];
+      const float g = gq[j] * (invp + (i == am ? 1.f : 0.f));
+      s1 += g;
+      s2 = fmaf(g, (x - c.mu) * c.istd, s2);
+      v[j * P + i] = g;
+    }
+  }
+  if (c.accum) {
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const float4 o = gs[k];
+      v[4 * k] += o.x;
+      v[4 * k + 1] += o.y;
+      v[4 * k + 2] += o.z;
+      v[4 * k + 3] += o.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NC; ++k) gs[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+template <int P>
+__device__ __forceinline__ void pool_route(const PwChan& c, long long soff, float4 gg, float& s1, float& s2) {
+  const float4* xs = reinterpret_cast<const float4*>(c.x + soff);
+  float4* gs = reinterpret_cast<float4*>(c.g + soff);
+  const float gq[4] = {gg.x, gg.y, gg.z, gg.w};
+  if constexpr (P == 8) {      // two halves: 16 source samples in registers at a time
+    pool_route_part<8, 2>(c, xs, gs, gq, s1, s2);
+    pool_route_part<8, 2>(c, xs + 4, gs + 4, gq + 2, s1, s2);
+  } else {
+    pool_route_part<P, 4>(c, xs, gs, gq, s1, s2);
+  }
+}
+
 // CTA-wide reduction of per-thread partial sums part[NV] -> double atomics.  red_s: [4][NV] floats.
 template <int NV, typename F>
 __device__ __forceinline__ void cta_reduce_atomic(float (&part)[NV], float* red_s, F&& sink) {
@@ -580,37 +646,11 @@ __global__ void __launch_bounds__(PW_NT, 4) pw_bwd_data_kernel(const __grid_cons
         float4 gg = (col & 1) ? make_float4(ap[0].y, ap[1].y, ap[2].y, ap[3].y) : make_float4(ap[0].x, ap[1].x, ap[2].x, ap[3].x);
         {
           // route the 4 pooled gradients to their 4*P source samples: g * (1/P + [first arg max])
-          const int P = op.pool;
-          const long long soff = (long long)n * c.nstride + (long long)l * P;
-          const float gq[4] = {gg.x, gg.y, gg.z, gg.w};
-          const float invp = 1.f / (float)P;
+          const long long soff = (long long)n * c.nstride + (long long)l * op.pool;
           float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float* xs = c.x + soff + j * P;
-            float* gs = c.g + soff + j * P;
-            int am = 0;
-            float mx = -INFINITY;
-            for (int i = 0; i < P; ++i) {
-              const float u = fmaf(c.sc, __ldg(xs + i), c.sh);
-              if (u > mx) {
-                mx = u;
-                am = i;
-              }
-            }
-            for (int i = 0; i < P; i += 2) {   // P is even: pairs keep the stores 8-byte wide
-              float2 g2 = make_float2(gq[j] * (invp + (i == am ? 1.f : 0.f)), gq[j] * (invp + (i + 1 == am ? 1.f : 0.f)));
-              const float2 x2 = __ldg(reinterpret_cast<const float2*>(xs + i));
-              s1 += g2.x + g2.y;
-              s2 = fmaf(g2.x, (x2.x - c.mu) * c.istd, fmaf(g2.y, (x2.y - c.mu) * c.istd, s2));
-              if (c.accum) {
-                const float2 old = *reinterpret_cast<const float2*>(gs + i);
-                g2.x += old.x;
-                g2.y += old.y;
-              }
-              *reinterpret_cast<float2*>(gs + i) = g2;
-            }
-          }
+          if (op.pool == 2) pool_route<2>(c, soff, gg, s1, s2);
+          else if (op.pool == 4) pool_route<4>(c, soff, gg, s1, s2);
+          else pool_route<8>(c, soff, gg, s1, s2);
           if (c.bn >= 0) {
             my_st[(2 * col) * 32] += s1;
             my_st[(2 * col + 1) * 32] += s2;
